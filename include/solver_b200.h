@@ -1,0 +1,168 @@
+/* solver_b200.h -- C-ABI of the B200-native sparse direct solver backend.
+ *
+ * Two layers, both plain C (no torch / C++ types in any signature):
+ *
+ *  (1) the plugin callbacks, one row in solver_lookup[]; the prototypes mirror
+ *      the reference's src/solver_cholmod.h:26-30 / src/solver_umfpack.h and
+ *      are called from src/solvers.c:451-452 (init), :479-480 (analyze),
+ *      :493-494 (factorize), :564 (evaluate), :461-462 (finalize);
+ *
+ *  (2) the shim below the wrapper (SURVEY.md 8b "Shim below the wrapper"):
+ *      host-C symbolic analysis (b200_analyze*) and the CUDA numeric context
+ *      (b200_ctx_*, b200_factor*, b200_solve*) that the callbacks drive and
+ *      that tests / bench.py bind with ctypes.
+ *
+ * There is no CPU fallback for factor/solve: if no CUDA device is usable the
+ * numeric entry points return B200_ERR_CUDA and the plugin callbacks abort().
+ */
+#ifndef SOLVER_B200_H
+#define SOLVER_B200_H
+
+#include <stdint.h>
+#include "mc_solver.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) --
+ * plugin callbacks (replace src/solver_cholmod.c:33-342 / solver_umfpack.c) */
+void solver_init_b200( solver_state_t* s );
+void solver_analyze_b200( solver_state_t* s, matrix_t* A );
+void solver_factorize_b200( solver_state_t* s, matrix_t* A );
+void solver_evaluate_b200( solver_state_t* s, matrix_t* b, matrix_t* x );
+void solver_finalize_b200( solver_state_t* s );
+
+/* capability word advertised in the table row */
+#define SOLVER_B200_CAPABILITIES ( SOLVES_FORMAT_CSC | SOLVES_BASE_ZERO | SOLVES_SQUARE_ONLY | \
+    SOLVES_UNSYMMETRIC | SOLVES_SYMMETRIC_UPPER_TRIANGULAR | SOLVES_DATA_TYPE_REAL_DOUBLE | SOLVES_RHS_DCOL )
+
+/* ------------------------------------------------------------------ (2) -- */
+enum { B200_OK = 0, B200_ERR_ARG = -1, B200_ERR_NOMEM = -2, B200_ERR_CUDA = -3,
+       B200_ERR_NOT_SPD = -4, B200_ERR_SINGULAR = -5, B200_ERR_STATE = -6 };
+
+/* factorization kinds */
+enum { B200_KIND_CHOLESKY = 0,   /* P A P' = L L'  (symmetric, upper-CSC input)        */
+       B200_KIND_LU = 1 };       /* P A P' = L U on the pattern of A+A', pivoting in fronts */
+
+/* ordering methods for b200_analyze_opts */
+enum { B200_ORDER_ND = 0, B200_ORDER_NATURAL = 1, B200_ORDER_GIVEN = 2 };
+
+typedef struct b200_options {
+  int ordering;          /* B200_ORDER_*                                          */
+  const int* user_perm;  /* B200_ORDER_GIVEN: perm[k] = original index of pivot k */
+  int nd_leaf;           /* ND recursion stops at this many vertices (default 96) */
+  int relax;             /* 1 = relaxed amalgamation (default), 0 = fundamental    */
+  int nrelax[3];         /* column thresholds (default 4,16,48)                    */
+  double zrelax[3];      /* zero-fraction thresholds (default 0.8,0.1,0.05)        */
+  int threads;           /* host threads for the ordering (0 = all)                */
+} b200_options_t;
+
+void b200_default_options( b200_options_t* o );
+
+/* Symbolic analysis result: host-resident, plain arrays so that tests can
+ * check etree / column counts / supernodes bit-exactly against the oracle. */
+typedef struct b200_symbolic {
+  int n;
+  int kind;              /* B200_KIND_*                                           */
+  int64_t nnzA;          /* stored entries of the input CSC                        */
+  int* perm;             /* [n]  new -> old                                        */
+  int* iperm;            /* [n]  old -> new                                        */
+  int* parent;           /* [n]  elimination tree of the permuted matrix (-1 root) */
+  int* colcount;         /* [n]  nnz(L(:,j)) incl. diagonal, exact (no relaxation) */
+  int64_t nnzL;          /* sum colcount                                           */
+  double flops;          /* sum colcount^2 (Cholesky; LU on the same pattern = 2x) */
+  int nfund;             /* fundamental supernodes                                 */
+  int ns;                /* supernodes after relaxed amalgamation                  */
+  int* sn_start;         /* [ns+1] first column of each supernode                  */
+  int* sn_parent;        /* [ns]   assembly tree (-1 root)                         */
+  int* sn_depth;         /* [ns]   distance to its root (roots: 0)                 */
+  int64_t* rowptr;       /* [ns+1] into rowidx                                     */
+  int* rowidx;           /* front row lists, sorted; first k_s entries = pivots    */
+  int* relidx;           /* same indexing; for i>=k_s: position in parent's front  */
+  int64_t* lptr;         /* [ns+1] panel offsets (f_s x k_s, column-major, ld f_s) */
+  int64_t* uptr;         /* [ns+1] LU only: offsets of the U' panels (same layout as L: uptr==lptr) */
+  int64_t* amap;         /* [nnzA] destination of every stored input entry: offset
+                            into L storage; for LU, entries of the strict upper
+                            part map into the U' panels as (offset | 1<<62);
+                            -1 = entry ignored                                     */
+  int64_t stored_nnzL;   /* lptr[ns]: entries actually stored (with relaxation)    */
+  double stored_flops;   /* flops executed on the relaxed structure                */
+  int maxfront;          /* largest front order                                    */
+  int maxdepth;          /* deepest level                                          */
+  int64_t cb_arena[2];   /* doubles needed by the two contribution-block arenas    */
+  int64_t* cbptr;        /* [ns] offset of the contribution block in its arena     */
+  double t_order, t_symbolic;  /* seconds spent in ordering / rest of the analysis */
+} b200_symbolic_t;
+
+/* A: n x n CSC, base 0, unsorted rows allowed, duplicates summed.
+ * kind CHOLESKY: only entries with row <= col are used (upper triangle, as the
+ * dispatcher delivers for SOLVES_SYMMETRIC_UPPER_TRIANGULAR, src/solvers.c:42-92);
+ * kind LU: full matrix. Values are not read ("doesn't care about the actual
+ * values", src/solvers.h:95). Returns NULL on failure. */
+b200_symbolic_t* b200_analyze( int n, const unsigned int* colptr, const unsigned int* rowidx,
+                               int kind, const b200_options_t* opts );
+void b200_symbolic_free( b200_symbolic_t* S );
+
+/* standalone pieces of the analysis (exported for parity tests) */
+int b200_order_nd( int n, const int* xadj, const int* adj, int leaf, int threads, int* perm );
+int b200_etree( int n, const int* colptr, const int* rowidx, int* parent ); /* upper-CSC pattern */
+
+/* ---- numeric context (CUDA, sm_100a) */
+typedef struct b200_ctx b200_ctx_t;
+
+b200_ctx_t* b200_ctx_create( int device );       /* NULL if no usable device */
+void b200_ctx_destroy( b200_ctx_t* c );
+const char* b200_last_error( void );
+
+/* copy the symbolic structure to the device and build the static launch schedule */
+int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S );
+
+/* numeric factorization; vals = the nnzA stored values in input order.
+ * _host: pageable/pinned host pointer (H2D inside); _device: already in HBM. */
+int b200_factor_host( b200_ctx_t* c, const double* vals );
+int b200_factor_device( b200_ctx_t* c, const double* d_vals );
+
+/* x = A^{-1} b for p right-hand sides, column-major n x p, ld = n */
+int b200_solve_host( b200_ctx_t* c, const double* b, int p, double* x );
+int b200_solve_device( b200_ctx_t* c, const double* d_b, int p, double* d_x );
+
+/* device memory helpers for callers without a CUDA runtime binding (bench.py, tests) */
+void* b200_dev_alloc( b200_ctx_t* c, size_t bytes );
+void b200_dev_free( b200_ctx_t* c, void* p );
+int b200_dev_upload( b200_ctx_t* c, void* dst, const void* src, size_t bytes );
+int b200_dev_download( b200_ctx_t* c, void* dst, const void* src, size_t bytes );
+void* b200_host_alloc_pinned( size_t bytes );
+void b200_host_free_pinned( void* p );
+int b200_dev_sync( b200_ctx_t* c );
+int b200_flush_l2( b200_ctx_t* c );             /* write a >L2 buffer between timed steps */
+
+/* statistics of the last factor / solve (device-event milliseconds) */
+typedef struct b200_stats {
+  double factor_ms;        /* whole factor on the device (events)            */
+  double solve_ms;         /* whole solve on the device (events)             */
+  double gemm_ms;          /* time in the DMMA trailing-update kernel        */
+  double gemm_flops;       /* flops executed by that kernel                  */
+  int64_t launches;        /* kernels launched by the last factor            */
+  int64_t solve_launches;  /* kernels launched by the last solve             */
+  int64_t gemm_launches;
+  double h2d_ms, d2h_ms;
+  int64_t device_bytes;    /* bytes of HBM held by the context               */
+  int npiv_perturbed;      /* LU: statically perturbed pivots                */
+} b200_stats_t;
+int b200_get_stats( b200_ctx_t* c, b200_stats_t* out );
+/* per-kernel timing of the next factor (serialises launches; diagnostics only) */
+int b200_set_profile( b200_ctx_t* c, int on );
+int b200_get_profile( b200_ctx_t* c, char* buf, size_t len );
+
+/* diagnostics for the parity tests: read back factor storage (0 = L panels, 1 = U' panels, 2 = inverse blocks) */
+int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count );
+
+/* micro-benchmarks used to establish the FP64 roof on the box */
+double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ); /* our DMMA kernel */
+double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

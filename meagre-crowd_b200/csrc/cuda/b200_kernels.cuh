@@ -1,0 +1,624 @@
+/* b200_kernels.cuh -- device kernels of the multifrontal factor / solve (sm_100a).
+ *
+ * The numeric work the reference hands to cholmod_factorize / cholmod_solve
+ * (src/solver_cholmod.c:272,303), umfpack_di_numeric / _solve
+ * (src/solver_umfpack.c:98,133) and dmumps_c JOB=2/3 (src/solver_mumps.c:211-213,
+ * 274-276) is done here by hand-written kernels:
+ *
+ *   scatter_A          CSC values -> frontal panels through the analysis map   (HBM bound)
+ *   extend_add         child contribution blocks -> parent front, by parent
+ *                      column block so that no atomics are needed               (HBM bound)
+ *   potrf_diag         <=64x64 diagonal block Cholesky + triangular inverse     (latency)
+ *   getrf_diag         <=64x64 diagonal block LU, partial pivoting inside it   (latency)
+ *   trsm_rows          panel rows x inverse diagonal block                     (FP64)
+ *   gemm_nt_dmma       C -= A * B'  on FP64 tensor-core tiles
+ *                      (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no
+ *                      f64 kind), operands staged with cp.async multi-stage    (FP64 roof)
+ *   solve kernels      level-set forward/backward sweeps over supernode blocks (HBM bound)
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int NB = 64;        /* diagonal block / inner panel width */
+constexpr int POTRF_SMEM = ( 2 * NB * ( NB + 1 ) + NB ) * 8;
+constexpr int GETRF_SMEM = ( 3 * NB * ( NB + 1 ) + 2 * NB ) * 8;
+constexpr int TRSM_SMEM = ( NB * NB + NB * 128 ) * 8;
+
+/* ------------------------------------------------------------------ tasks */
+struct GemmTask {
+  double* C; const double* A; const double* B;
+  int ldc, lda, ldb;
+  int M, N, K;
+  int lower;   /* 1: store only elements with r + diag >= c */
+  int diag;    /* (first row of C in the front) - (first col of C in the front) */
+};
+struct Tile { int task; unsigned short tm, tn; };
+
+struct DiagTask {
+  double* A; double* AU; int lda; int nb;   /* A: block in the L panel; AU: same block of the U' panel (LU) */
+  double* inv;      /* nb x nb, ld nb: inverse of L (Cholesky) / of unit-L (LU)      */
+  double* inv2;     /* LU: inverse of U, stored transposed                            */
+  int* piv;         /* LU: pivot row (block-local) chosen for each column            */
+  int col;          /* global column of the block (for error reports)                */
+};
+
+struct TrsmTask {
+  double* B; int ldb; int m;     /* m rows starting at B, nb columns */
+  const double* T; int nb;       /* X = B * T'   (T nb x nb, ld nb)  */
+  const int* piv;                /* LU U-panel: permute the nb columns of B on load (NULL = none) */
+};
+struct RowTile { int task; int r0; };
+
+struct AsmTask { int parent; int col0; int ncols; };
+
+struct SnMeta {           /* per supernode, device copy */
+  int64_t lptr, uptr, cbptr, rowptr, invptr;
+  int c0, k, f, parent, depth, child_begin, child_end, pad;
+  int64_t wptr;           /* solve workspace row offset within its level arena */
+};
+
+struct SolveBlk { int sn; int j0; int nb; int first_partial; int ntiles; int pad; };
+
+/* ---------------------------------------------------------- small helpers */
+__device__ __forceinline__ void cp_async8( void* smem, const void* g, int src_bytes ) {
+  unsigned s = ( unsigned )__cvta_generic_to_shared( smem );
+  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"( s ), "l"( g ), "r"( src_bytes ) );
+}
+__device__ __forceinline__ void cp_async16( void* smem, const void* g, int src_bytes ) {
+  unsigned s = ( unsigned )__cvta_generic_to_shared( smem );
+  asm volatile( "cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"( s ), "l"( g ), "r"( src_bytes ) );
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile( "cp.async.wait_group %0;\n" ::"n"( N ) ); }
+
+__device__ __forceinline__ void dmma884( double& d0, double& d1, double a, double b ) {
+  asm volatile( "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"( d0 ), "+d"( d1 ) : "d"( a ), "d"( b ) );
+}
+
+/* ------------------------------------------------------------- scatter A */
+__global__ void scatter_A_kernel( const double* __restrict__ vals, const int64_t* __restrict__ amap, int64_t nnz,
+                                  double* __restrict__ L, double* __restrict__ U ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < nnz; e += stride ) {
+    int64_t d = amap[e];
+    if ( d < 0 ) continue;
+    double v = vals[e];
+    if ( d & ( ( int64_t )1 << 62 ) ) atomicAdd( &U[d & ~( ( int64_t )1 << 62 )], v );
+    else atomicAdd( &L[d], v );
+  }
+}
+
+/* ------------------------------------------------------------ extend-add
+ * One CTA per (parent, block of destination columns); inside it each warp owns
+ * a fixed subset of those columns.  Children are visited in a fixed order and
+ * each child touches a destination column at most once, so the sums are
+ * deterministic without atomics or barriers.  Lanes run down a source column
+ * (coalesced 8-byte reads); destination rows are monotone in the lane index. */
+template <bool LU>
+__global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __restrict__ tasks, const SnMeta* __restrict__ sn,
+                                                            const int* __restrict__ child_list, const int* __restrict__ relidx,
+                                                            double* __restrict__ L, double* __restrict__ U,
+                                                            double* __restrict__ cb_parent, const double* __restrict__ cb_child ) {
+  const AsmTask t = tasks[blockIdx.x];
+  const SnMeta P = sn[t.parent];
+  const int kp = P.k, fp = P.f, up = fp - kp;
+  double* Lp = L + P.lptr;
+  double* Up = LU ? U + P.uptr : nullptr;
+  double* CBp = cb_parent + P.cbptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int lo = t.col0, hi = t.col0 + t.ncols;
+  for ( int ci = P.child_begin; ci < P.child_end; ci++ ) {
+    const SnMeta C = sn[child_list[ci]];
+    const int uc = C.f - C.k;
+    if ( uc == 0 ) continue;
+    const int* rel = relidx + C.rowptr + C.k;
+    const double* src = cb_child + C.cbptr;
+    /* range [a,b) of child columns whose destination column is in [lo,hi): rel is increasing */
+    int a = 0, b = uc;
+    { int x = 0, y = uc; while ( x < y ) { int m = ( x + y ) >> 1; if ( rel[m] < lo ) x = m + 1; else y = m; } a = x; }
+    { int x = a, y = uc; while ( x < y ) { int m = ( x + y ) >> 1; if ( rel[m] < hi ) x = m + 1; else y = m; } b = x; }
+    for ( int j = a; j < b; j++ ) {
+      const int dj = rel[j];
+      /* a destination column belongs to exactly one warp, whichever child feeds it:
+       * children can then be processed back to back without a barrier */
+      if ( ( ( dj - lo ) & ( nwarps - 1 ) ) != warp ) continue;
+      const double* s = src + ( int64_t )j * uc;
+      if ( !LU ) {
+        /* lower triangle only: i >= j, hence rel[i] >= dj */
+        if ( dj < kp ) {
+          double* d = Lp + ( int64_t )dj * fp;
+          for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
+        } else {
+          double* d = CBp + ( int64_t )( dj - kp ) * up - kp;
+          for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
+        }
+      } else {
+        /* full block: (di,dj) goes to the L panel (di>=dj, dj pivot), the U' panel
+         * (di<dj, di pivot; stored transposed) or the parent's contribution block */
+        for ( int i = lane; i < uc; i += 32 ) {
+          const int di = rel[i];
+          const double v = s[i];
+          if ( di >= dj ) { if ( dj < kp ) Lp[( int64_t )dj * fp + di] += v; else CBp[( int64_t )( dj - kp ) * up + ( di - kp )] += v; }
+          else { if ( di < kp ) Up[( int64_t )di * fp + dj] += v; else CBp[( int64_t )( dj - kp ) * up + ( di - kp )] += v; }
+        }
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------- diagonal block: LL'
+ * Right-looking Cholesky of an nb x nb (nb<=64) block held in shared memory,
+ * then the inverse of the triangular factor (used by trsm_rows and the solves). */
+__global__ void __launch_bounds__( 256 ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
+  extern __shared__ double dsm[];
+  double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
+  double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
+  double* colv = dsm + 2 * NB * ( NB + 1 );
+  const DiagTask t = tasks[blockIdx.x];
+  const int nb = t.nb, tid = threadIdx.x;
+  for ( int e = tid; e < nb * nb; e += 256 ) { int r = e % nb, c = e / nb; a[r][c] = ( r >= c ) ? t.A[r + ( int64_t )c * t.lda] : 0.0; x[r][c] = 0.0; }
+  __syncthreads();
+  for ( int j = 0; j < nb; j++ ) {
+    double d = a[j][j];
+    if ( !( d > 0.0 ) ) { if ( tid == 0 ) atomicCAS( err, 0, t.col + j + 1 ); d = 1.0; }
+    const double s = sqrt( d );
+    if ( tid < nb ) colv[tid] = tid > j ? a[tid][j] / s : ( tid == j ? s : 0.0 );
+    __syncthreads();
+    if ( tid < nb && tid >= j ) a[tid][j] = colv[tid];
+    /* trailing update of the lower triangle, columns j+1.. */
+    const int r = tid & 63, cg = tid >> 6;
+    if ( r < nb && r > j ) {
+      const double lr = colv[r];
+      for ( int c = j + 1 + cg; c <= r; c += 4 ) a[r][c] -= lr * colv[c];
+    }
+    __syncthreads();
+  }
+  /* inverse of lower-triangular a: four lanes per column, split over q */
+  {
+    const int col = tid >> 2, part = tid & 3;
+    if ( col < nb ) {
+      if ( part == 0 ) x[col][col] = 1.0 / a[col][col];
+    }
+    __syncwarp();
+    for ( int i = 1; i < nb; i++ ) {
+      double s = 0.0;
+      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) s += a[i][q] * x[q][col];
+      s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+      s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+      if ( col < nb && i > col && part == 0 ) x[i][col] = -s / a[i][i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for ( int e = tid; e < nb * nb; e += 256 ) {
+    int r = e % nb, c = e / nb;
+    if ( r >= c ) t.A[r + ( int64_t )c * t.lda] = a[r][c];
+    t.inv[r + c * nb] = x[r][c];
+  }
+}
+
+/* ------------------------------------------------------ diagonal block: LU
+ * LU of an nb x nb block with partial pivoting restricted to the block's own
+ * rows.  piv[j] = block-local row swapped into position j.  Tiny pivots are
+ * replaced by +-tiny (static perturbation) and counted.  Outputs: packed L\U
+ * in place, inv = inverse of unit-lower L, inv2 = (inverse of U) transposed. */
+__global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __restrict__ tasks, double tiny, int* __restrict__ nperturbed ) {
+  extern __shared__ double dsm[];
+  double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
+  double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
+  double ( *y )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + 2 * NB * ( NB + 1 ) );
+  double* colv = dsm + 3 * NB * ( NB + 1 );
+  double* rowv = colv + NB;
+  __shared__ int prow;
+  const DiagTask t = tasks[blockIdx.x];
+  const int nb = t.nb, tid = threadIdx.x;
+  for ( int e = tid; e < nb * nb; e += 256 ) { int r = e % nb, c = e / nb; a[r][c] = ( r >= c ) ? t.A[r + ( int64_t )c * t.lda] : t.AU[c + ( int64_t )r * t.lda]; x[r][c] = 0.0; y[r][c] = 0.0; }
+  __syncthreads();
+  for ( int j = 0; j < nb; j++ ) {
+    if ( tid < 32 ) { /* arg-max of |a[r][j]|, r>=j, first maximal row wins */
+      double best = -1.0; int bi = j;
+      for ( int r = j + tid; r < nb; r += 32 ) { double v = fabs( a[r][j] ); if ( v > best ) { best = v; bi = r; } }
+      for ( int o = 16; o; o >>= 1 ) {
+        double ob = __shfl_xor_sync( 0xffffffffu, best, o ); int oi = __shfl_xor_sync( 0xffffffffu, bi, o );
+        if ( ob > best || ( ob == best && oi < bi ) ) { best = ob; bi = oi; }
+      }
+      if ( tid == 0 ) { prow = bi; t.piv[j] = bi; }
+    }
+    __syncthreads();
+    const int p = prow;
+    if ( p != j && tid < nb ) { double tmp = a[j][tid]; a[j][tid] = a[p][tid]; a[p][tid] = tmp; }
+    __syncthreads();
+    double d = a[j][j];
+    if ( !( fabs( d ) > tiny ) ) { d = ( d < 0.0 ) ? -tiny : tiny; if ( tid == 0 ) { a[j][j] = d; atomicAdd( nperturbed, 1 ); } }
+    if ( tid < nb ) { colv[tid] = tid > j ? a[tid][j] / d : 0.0; rowv[tid] = tid > j ? a[j][tid] : 0.0; }
+    __syncthreads();
+    if ( tid < nb && tid > j ) a[tid][j] = colv[tid];
+    const int r = tid & 63, cg = tid >> 6;
+    if ( r < nb && r > j ) {
+      const double lr = colv[r];
+      for ( int c = j + 1 + cg; c < nb; c += 4 ) a[r][c] -= lr * rowv[c];
+    }
+    __syncthreads();
+  }
+  /* x = inverse of unit lower L ; y = inverse of upper U (column by column of the transposes) */
+  {
+    const int col = tid >> 2, part = tid & 3;
+    if ( col < nb && part == 0 ) { x[col][col] = 1.0; y[col][col] = 1.0 / a[col][col]; }
+    __syncwarp();
+    for ( int i = 1; i < nb; i++ ) {
+      double s = 0.0, u = 0.0;
+      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) { s += a[i][q] * x[q][col]; u += a[q][i] * y[col][q]; }
+      s += __shfl_xor_sync( 0xffffffffu, s, 1 ); s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+      u += __shfl_xor_sync( 0xffffffffu, u, 1 ); u += __shfl_xor_sync( 0xffffffffu, u, 2 );
+      if ( col < nb && i > col && part == 0 ) { x[i][col] = -s; y[col][i] = -u / a[i][i]; }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for ( int e = tid; e < nb * nb; e += 256 ) {
+    int r = e % nb, c = e / nb;
+    if ( r > c ) t.A[r + ( int64_t )c * t.lda] = a[r][c];          /* unit-lower L, strict part   */
+    else t.AU[c + ( int64_t )r * t.lda] = a[r][c];                 /* U (incl. diagonal), as U'   */
+    if ( r == c ) t.A[r + ( int64_t )c * t.lda] = 1.0;
+    t.inv[r + c * nb] = x[r][c];     /* inv(L), lower                                  */
+    t.inv2[r + c * nb] = y[c][r];    /* inv(U)' : y holds inv(U) (upper), store transpose */
+  }
+}
+
+/* -------------------------------------------------------------- trsm rows
+ * X = B * T' for a tile of 128 rows; T (nb x nb) is lower triangular, so column
+ * c of X needs q <= c only.  B is overwritten.  4x8 register tile per thread. */
+__global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __restrict__ tasks, const RowTile* __restrict__ tiles ) {
+  extern __shared__ double sm[];
+  const RowTile rt = tiles[blockIdx.x];
+  const TrsmTask t = tasks[rt.task];
+  const int nb = t.nb;
+  double* Ts = sm;                 /* [q][c]  stride NB   : T[c,q]  */
+  double* Bs = sm + NB * NB;       /* [q][r]  stride 128            */
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = min( 128, t.m - rt.r0 );
+  double* Bg = t.B + rt.r0;
+  for ( int e = tid; e < NB * NB; e += 256 ) { int c = e % NB, q = e / NB; Ts[q * NB + c] = ( c < nb && q < nb ) ? t.T[c + q * nb] : 0.0; }
+  for ( int e = tid; e < nb * 128; e += 256 ) {
+    int r = e & 127, q = e >> 7;
+    Bs[q * 128 + r] = ( r < rows ) ? Bg[r + ( int64_t )q * t.ldb] : 0.0;
+  }
+  __syncthreads();
+  if ( t.piv ) { /* apply the block's row interchanges to the columns of this tile, in order */
+    for ( int j = 0; j < nb; j++ ) {
+      const int p = t.piv[j];
+      if ( p != j && tid < 128 ) { double tmp = Bs[j * 128 + tid]; Bs[j * 128 + tid] = Bs[p * 128 + tid]; Bs[p * 128 + tid] = tmp; }
+      __syncthreads();
+    }
+  }
+  double acc[4][8];
+#pragma unroll
+  for ( int i = 0; i < 4; i++ )
+#pragma unroll
+    for ( int j = 0; j < 8; j++ ) acc[i][j] = 0.0;
+  const int c0 = warp * 8;
+  if ( c0 < nb ) {
+    const int qend = min( nb, c0 + 8 );
+    for ( int q = 0; q < qend; q++ ) {
+      double bv[4], tv[8];
+#pragma unroll
+      for ( int i = 0; i < 4; i++ ) bv[i] = Bs[q * 128 + lane + 32 * i];
+#pragma unroll
+      for ( int j = 0; j < 8; j++ ) tv[j] = Ts[q * NB + c0 + j];
+#pragma unroll
+      for ( int i = 0; i < 4; i++ )
+#pragma unroll
+        for ( int j = 0; j < 8; j++ ) acc[i][j] += bv[i] * tv[j];
+    }
+#pragma unroll
+    for ( int j = 0; j < 8; j++ ) {
+      const int c = c0 + j;
+      if ( c < nb ) {
+#pragma unroll
+        for ( int i = 0; i < 4; i++ ) { const int r = lane + 32 * i; if ( r < rows ) Bg[r + ( int64_t )c * t.ldb] = acc[i][j]; }
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------------- DMMA GEMM NT
+ * C[M x N] -= A[M x K] * B[N x K]'   (all column-major).
+ * CTA tile BM x BN, K step 16, STAGES-deep cp.async pipeline.  Shared tiles are
+ * stored k-major with a row stride of BM+4 doubles so that the m8n8k4 fragment
+ * reads (lane>>2 -> m, lane&3 -> k) hit 32 distinct banks.  Each warp owns a
+ * WM x WN sub-tile = (WM/8)x(WN/8) DMMA.8x8x4 accumulators in registers. */
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles ) {
+  constexpr int BK = 16;
+  constexpr int NT = ( BM / WM ) * ( BN / WN ) * 32;
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  extern __shared__ double sm[];
+  double* As = sm;                         /* [STAGES][BK][LDA] */
+  double* Bs = sm + STAGES * BK * LDA;     /* [STAGES][BK][LDB] */
+  const Tile tl = tiles[blockIdx.x];
+  const GemmTask t = tasks[tl.task];
+  const int m0 = tl.tm * BM, n0 = tl.tn * BN;
+  const int mrem = t.M - m0, nrem = t.N - n0;
+  const double* Ag = t.A + m0;
+  const double* Bg = t.B + n0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
+  const bool a16 = ( ( ( uintptr_t )Ag & 15 ) == 0 ) && ( ( t.lda & 1 ) == 0 );
+  const bool b16 = ( ( ( uintptr_t )Bg & 15 ) == 0 ) && ( ( t.ldb & 1 ) == 0 );
+  const int K = t.K;
+  const int nk = ( K + BK - 1 ) / BK;
+
+  auto load_stage = [&]( int stage, int k0 ) {
+    double* as = As + stage * BK * LDA;
+    double* bs = Bs + stage * BK * LDB;
+    if ( a16 ) {
+      for ( int c = tid; c < BK * BM / 2; c += NT ) {
+        const int q = c / ( BM / 2 ), r = ( c % ( BM / 2 ) ) * 2;
+        const int kq = k0 + q;
+        int bytes = ( kq < K ) ? max( 0, min( 2, mrem - r ) ) * 8 : 0;
+        cp_async16( as + q * LDA + r, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
+      }
+    } else {
+      for ( int c = tid; c < BK * BM; c += NT ) {
+        const int q = c / BM, r = c % BM;
+        const int kq = k0 + q;
+        int bytes = ( kq < K && r < mrem ) ? 8 : 0;
+        cp_async8( as + q * LDA + r, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
+      }
+    }
+    if ( b16 ) {
+      for ( int c = tid; c < BK * BN / 2; c += NT ) {
+        const int q = c / ( BN / 2 ), r = ( c % ( BN / 2 ) ) * 2;
+        const int kq = k0 + q;
+        int bytes = ( kq < K ) ? max( 0, min( 2, nrem - r ) ) * 8 : 0;
+        cp_async16( bs + q * LDB + r, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
+      }
+    } else {
+      for ( int c = tid; c < BK * BN; c += NT ) {
+        const int q = c / BN, r = c % BN;
+        const int kq = k0 + q;
+        int bytes = ( kq < K && r < nrem ) ? 8 : 0;
+        cp_async8( bs + q * LDB + r, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
+      }
+    }
+  };
+
+  double acc[MT][NTL][2];
+#pragma unroll
+  for ( int i = 0; i < MT; i++ )
+#pragma unroll
+    for ( int j = 0; j < NTL; j++ ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+  for ( int s = 0; s < STAGES - 1; s++ ) { if ( s < nk ) load_stage( s, s * BK ); cp_async_commit(); }
+
+  const int fr = lane >> 2, fk = lane & 3;
+  for ( int kt = 0; kt < nk; kt++ ) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    { const int nx = kt + STAGES - 1; if ( nx < nk ) load_stage( nx % STAGES, nx * BK ); cp_async_commit(); }
+    const double* as = As + ( kt % STAGES ) * BK * LDA + wm0 + fr;
+    const double* bs = Bs + ( kt % STAGES ) * BK * LDB + wn0 + fr;
+#pragma unroll
+    for ( int kk = 0; kk < BK; kk += 4 ) {
+      double af[MT], bf[NTL];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
+#pragma unroll
+      for ( int j = 0; j < NTL; j++ ) bf[j] = bs[( kk + fk ) * LDB + j * 8];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ )
+#pragma unroll
+        for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
+    }
+  }
+  cp_async_wait<0>();
+
+  /* epilogue: C -= acc (read-modify-write, masked to the stored triangle) */
+  double* Cg = t.C;
+#pragma unroll
+  for ( int j = 0; j < NTL; j++ ) {
+#pragma unroll
+    for ( int h = 0; h < 2; h++ ) {
+      const int c = n0 + wn0 + j * 8 + 2 * fk + h;
+      if ( c < t.N ) {
+        double* cc = Cg + ( int64_t )c * t.ldc;
+#pragma unroll
+        for ( int i = 0; i < MT; i++ ) {
+          const int r = m0 + wm0 + i * 8 + fr;
+          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) cc[r] -= acc[i][j][h];
+        }
+      }
+    }
+  }
+}
+
+/* -------------------------------------------------------------- solves */
+constexpr int PC = 8;   /* right-hand sides per pass */
+
+__global__ void permute_in_kernel( const double* __restrict__ b, const int* __restrict__ perm, int n, int p, double* __restrict__ y ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < tot; e += stride ) { int k = ( int )( e % n ); int64_t c = e / n; y[e] = b[perm[k] + c * n]; }
+}
+__global__ void permute_out_kernel( const double* __restrict__ y, const int* __restrict__ perm, int n, int p, double* __restrict__ x ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < tot; e += stride ) { int k = ( int )( e % n ); int64_t c = e / n; x[perm[k] + c * n] = y[e]; }
+}
+
+/* forward: add the children's update vectors into the parent's pivots (y) and update rows (w) */
+__global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const int* __restrict__ parents, const SnMeta* __restrict__ sn, const int* __restrict__ child_list,
+                                                            const int* __restrict__ relidx, double* __restrict__ y, int n, int p,
+                                                            double* __restrict__ w_parent, int64_t ldw_parent, const double* __restrict__ w_child, int64_t ldw_child ) {
+  const SnMeta P = sn[parents[blockIdx.x]];
+  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
+  for ( int ci = P.child_begin; ci < P.child_end; ci++ ) {
+    const SnMeta C = sn[child_list[ci]];
+    const int uc = C.f - C.k;
+    const int* rel = relidx + C.rowptr + C.k;
+    for ( int i = threadIdx.x; i < uc; i += blockDim.x ) {
+      const int d = rel[i];
+      for ( int q = 0; q < pcn; q++ ) {
+        const double v = w_child[C.wptr + i + ( int64_t )( pc0 + q ) * ldw_child];
+        if ( d < P.k ) y[P.c0 + d + ( int64_t )( pc0 + q ) * n] += v;
+        else w_parent[P.wptr + ( d - P.k ) + ( int64_t )( pc0 + q ) * ldw_parent] += v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+/* z = T * P * y_b  (T = inverse of the block's lower factor), written back in place */
+__global__ void __launch_bounds__( 64 ) fwd_diag_kernel( const SolveBlk* __restrict__ blks, const SnMeta* __restrict__ sn, const double* __restrict__ inv,
+                                                         const int* __restrict__ piv, double* __restrict__ y, int n, int p ) {
+  __shared__ double ys[NB][PC];
+  const SolveBlk b = blks[blockIdx.x];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
+  const int r = threadIdx.x, nb = b.nb;
+  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
+  double* yb = y + S.c0 + b.j0;
+  if ( r < nb ) for ( int q = 0; q < pcn; q++ ) ys[r][q] = yb[r + ( int64_t )( pc0 + q ) * n];
+  __syncthreads();
+  if ( piv ) {
+    if ( r < pcn ) { const int* pv = piv + S.c0 + b.j0; for ( int j = 0; j < nb; j++ ) { int pj = pv[j]; if ( pj != j ) { double t = ys[j][r]; ys[j][r] = ys[pj][r]; ys[pj][r] = t; } } }
+    __syncthreads();
+  }
+  if ( r < nb ) {
+    double acc[PC];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+    for ( int c = 0; c <= r; c++ ) {
+      const double tv = T[r + c * nb];
+#pragma unroll
+      for ( int q = 0; q < PC; q++ ) acc[q] += tv * ys[c][q];
+    }
+    for ( int q = 0; q < pcn; q++ ) yb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
+  }
+}
+
+/* rows below the block: y/w -= L[rows, block] * z ; one thread per row, 256 rows per CTA */
+__global__ void __launch_bounds__( 256 ) fwd_update_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                            const double* __restrict__ L, double* __restrict__ y, int n, int p,
+                                                            double* __restrict__ w, int64_t ldw ) {
+  __shared__ double zs[NB][PC];
+  const RowTile rt = tiles[blockIdx.x];
+  const SolveBlk b = blks[rt.task];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
+  const int nb = b.nb;
+  for ( int e = threadIdx.x; e < nb * PC; e += 256 ) { int r = e / PC, q = e % PC; zs[r][q] = q < pcn ? y[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] : 0.0; }
+  __syncthreads();
+  const int lr = b.j0 + nb + rt.r0 + threadIdx.x;   /* front-local row */
+  if ( lr >= S.f ) return;
+  const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.f;
+  double acc[PC];
+#pragma unroll
+  for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+  for ( int c = 0; c < nb; c++ ) {
+    const double lv = Lr[( int64_t )c * S.f];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) acc[q] += lv * zs[c][q];
+  }
+  if ( lr < S.k ) { for ( int q = 0; q < pcn; q++ ) y[S.c0 + lr + ( int64_t )( pc0 + q ) * n] -= acc[q]; }
+  else { for ( int q = 0; q < pcn; q++ ) w[S.wptr + ( lr - S.k ) + ( int64_t )( pc0 + q ) * ldw] -= acc[q]; }
+}
+
+/* backward, stage 1: partial[tile][c][q] = sum over the tile's rows of M[row, block col c] * x[row]
+ * M = L panel (Cholesky: L' x) or the U' panel / pivot-block rows (LU). 1024 rows per CTA;
+ * each warp owns block columns c = warp, warp+8, ..; lanes stride over rows (coalesced). */
+constexpr int BWD_ROWS = 1024;
+template <bool LU>
+__global__ void __launch_bounds__( 256 ) bwd_partial_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                             const double* __restrict__ L, const double* __restrict__ U, const int* __restrict__ rowidx,
+                                                             const double* __restrict__ x, int n, int p, double* __restrict__ partial ) {
+  __shared__ double xs[PC / 2][BWD_ROWS];   /* two passes of PC/2 right-hand sides keep this at 32 KB */
+  const RowTile rt = tiles[blockIdx.x];
+  const SolveBlk b = blks[rt.task];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
+  const int nb = b.nb, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = b.j0 + nb + rt.r0;                     /* first front-local row of the tile */
+  const int rows = min( BWD_ROWS, S.f - base );
+  const int tile_in_blk = rt.r0 / BWD_ROWS;
+  double* out = partial + ( ( int64_t )( b.first_partial + tile_in_blk ) * gridDim.y + blockIdx.y ) * NB * PC;
+  const int* ri = rowidx + S.rowptr;
+  for ( int half = 0; half < 2; half++ ) {
+    const int h0 = half * ( PC / 2 );
+    __syncthreads();
+    for ( int e = threadIdx.x; e < rows * ( PC / 2 ); e += 256 ) {
+      const int r = e % rows, q = e / rows;
+      const int lr = base + r;
+      const int g = lr < S.k ? S.c0 + lr : ri[lr];
+      xs[q][r] = ( h0 + q < pcn ) ? x[g + ( int64_t )( pc0 + h0 + q ) * n] : 0.0;
+    }
+    __syncthreads();
+    for ( int c = warp; c < nb; c += 8 ) {
+      double acc[PC / 2];
+#pragma unroll
+      for ( int q = 0; q < PC / 2; q++ ) acc[q] = 0.0;
+      {
+        /* Cholesky: column of the L panel (L' x).  LU: the same column of the U' panel (U x). */
+        const double* col = ( LU ? U : L ) + S.lptr + base + ( int64_t )( b.j0 + c ) * S.f;
+        for ( int r = lane; r < rows; r += 32 ) {
+          const double lv = col[r];
+#pragma unroll
+          for ( int q = 0; q < PC / 2; q++ ) acc[q] += lv * xs[q][r];
+        }
+      }
+#pragma unroll
+      for ( int q = 0; q < PC / 2; q++ ) {
+        double v = acc[q];
+        for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+        if ( lane == 0 ) out[c * PC + h0 + q] = v;
+      }
+    }
+  }
+}
+
+/* backward, stage 2: x_b = T' (y_b - sum of partials)   (Cholesky: T = inv(L); LU: T' = inv(U), stored transposed) */
+__global__ void __launch_bounds__( 64 ) bwd_diag_kernel( const SolveBlk* __restrict__ blks, const SnMeta* __restrict__ sn, const double* __restrict__ inv,
+                                                         double* __restrict__ x, int n, int p, const double* __restrict__ partial ) {
+  __shared__ double rs[NB][PC];
+  const SolveBlk b = blks[blockIdx.x];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
+  const int r = threadIdx.x, nb = b.nb;
+  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
+  double* xb = x + S.c0 + b.j0;
+  if ( r < nb ) {
+    for ( int q = 0; q < PC; q++ ) {
+      double v = q < pcn ? xb[r + ( int64_t )( pc0 + q ) * n] : 0.0;
+      for ( int t = 0; t < b.ntiles; t++ ) v -= partial[( ( int64_t )( b.first_partial + t ) * gridDim.y + blockIdx.y ) * NB * PC + r * PC + q];
+      rs[r][q] = v;
+    }
+  }
+  __syncthreads();
+  if ( r < nb ) {
+    double acc[PC];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+    for ( int c = r; c < nb; c++ ) {       /* x[r] = sum_{c>=r} T[c,r] rs[c] */
+      const double tv = T[c + r * nb];
+#pragma unroll
+      for ( int q = 0; q < PC; q++ ) acc[q] += tv * rs[c][q];
+    }
+    for ( int q = 0; q < pcn; q++ ) xb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
+  }
+}
+
+/* micro-benchmark: plain streaming copy */
+__global__ void stream_copy_kernel( const double2* __restrict__ a, double2* __restrict__ b, int64_t n2 ) {
+  int64_t i = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; i < n2; i += stride ) b[i] = a[i];
+}
+
+} /* namespace b200 */

@@ -1,0 +1,629 @@
+/* b200_numeric.cu -- CUDA context, static launch schedule, factor and solve drivers.
+ *
+ * extern "C" shim below the plugin wrapper: the host-C analysis
+ * hands over a b200_symbolic_t; everything that depends only on the pattern
+ * (task lists, tile lists, launch order) is built ONCE here at upload time, so
+ * that factorize (src/solvers.c:485-495 -> table.factorize) and evaluate
+ * (src/solvers.c:500-611 -> table.evaluate) are pure replays of kernel launches
+ * with no host-side decisions and no device->host round trips inside the loop.
+ *
+ * Data layout in HBM (all FP64, column-major):
+ *   L      : one f_s x k_s panel per supernode at lptr[s]            (permanent)
+ *   U'     : LU only, same layout as L (upper factor stored transposed)
+ *   CB[2]  : contribution blocks u_s x u_s of one tree level, double-buffered
+ *            by level parity; level d reads CB[(d+1)&1], writes CB[d&1]
+ *   inv    : inverse of every <=64x64 diagonal block (and of U's for LU)
+ */
+#include <cuda_runtime.h>
+#include <vector>
+#include <algorithm>
+#include <string>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include "solver_b200.h"
+#include "b200_kernels.cuh"
+
+using namespace b200;
+
+static thread_local char g_err[512] = "";
+static int set_err( const char* fmt, const char* a = "", const char* b = "" ) { snprintf( g_err, sizeof( g_err ), fmt, a, b ); return B200_ERR_CUDA; }
+extern "C" const char* b200_last_error( void ) { return g_err; }
+
+#define CK( call ) do { cudaError_t e_ = ( call ); if ( e_ != cudaSuccess ) { set_err( "%s: %s", #call, cudaGetErrorString( e_ ) ); return B200_ERR_CUDA; } } while ( 0 )
+#define CKN( call ) do { cudaError_t e_ = ( call ); if ( e_ != cudaSuccess ) { set_err( "%s: %s", #call, cudaGetErrorString( e_ ) ); return nullptr; } } while ( 0 )
+
+constexpr int NBO = 256;      /* outer panel width: K of the big trailing update */
+constexpr int ASM_COLS = 32;  /* destination columns per extend-add CTA */
+constexpr int GEMM_STAGES = 4;
+constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 132 + 132 ) * 8;
+constexpr int SMALL_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
+
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma_128", "gemm_dmma_64" };
+
+struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; };
+
+/* solve schedule */
+enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_DIAG, SK_FWD_UPDATE, SK_BWD_PARTIAL, SK_BWD_DIAG, SK_COUNT };
+struct SLaunch { int kind; int64_t first; int64_t count; int64_t first_tile; int64_t ntiles; int depth; };
+
+template <class T> struct DevVec {
+  T* d = nullptr; size_t n = 0;
+  int upload( const std::vector<T>& h ) {
+    n = h.size();
+    if ( n == 0 ) return 0;
+    CK( cudaMalloc( &d, n * sizeof( T ) ) );
+    CK( cudaMemcpy( d, h.data(), n * sizeof( T ), cudaMemcpyHostToDevice ) );
+    return 0;
+  }
+  void release() { if ( d ) cudaFree( d ); d = nullptr; n = 0; }
+  size_t bytes() const { return n * sizeof( T ); }
+};
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop;
+  /* symbolic copy */
+  int n = 0, ns = 0, kind = 0, maxdepth = 0;
+  int64_t nnzA = 0, lsize = 0, invsize = 0;
+  int64_t cb_arena[2] = { 0, 0 };
+  std::vector<int64_t> level_cb;          /* doubles of CB used by each level */
+  std::vector<int64_t> level_w;           /* solve workspace rows per level */
+  int64_t w_rows[2] = { 0, 0 };
+  double flops_exact = 0, flops_stored = 0;
+  /* device arrays */
+  double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr;
+  DevVec<int64_t> amap; DevVec<int> perm, rowidx, relidx, child_list;
+  DevVec<SnMeta> sn;
+  DevVec<GemmTask> gemm_tasks; DevVec<Tile> tiles_big, tiles_small;
+  DevVec<DiagTask> diag_tasks; DevVec<TrsmTask> trsm_tasks; DevVec<RowTile> trsm_tiles;
+  DevVec<AsmTask> asm_tasks;
+  std::vector<Launch> launches;
+  /* solve */
+  DevVec<SolveBlk> sblk; DevVec<RowTile> fwd_tiles, bwd_tiles; DevVec<int> gather_parents;
+  std::vector<SLaunch> slaunches;
+  int64_t max_partial_tiles = 0;
+  double *dY = nullptr, *dW[2] = { nullptr, nullptr }, *dPartial = nullptr, *dB = nullptr, *dX = nullptr;
+  int solve_p_cap = 0, io_p_cap = 0;
+  void* flush_buf = nullptr; size_t flush_bytes = 0;
+  bool factored = false;
+  bool profile = false;
+  double prof_ms[LK_COUNT] = { 0 }; int64_t prof_n[LK_COUNT] = { 0 };
+  double tiny = 0.0;
+  b200_stats_t stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+  int64_t device_bytes = 0;
+};
+
+/* ------------------------------------------------------------ context */
+extern "C" b200_ctx_t* b200_ctx_create( int device ) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount( &ndev );
+  if ( e != cudaSuccess || ndev == 0 ) { set_err( "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString( e ) : "device count is 0" ); return nullptr; }
+  if ( device < 0 || device >= ndev ) { set_err( "bad device index%s", "" ); return nullptr; }
+  CKN( cudaSetDevice( device ) );
+  b200_ctx* c = new b200_ctx();
+  c->device = device;
+  CKN( cudaGetDeviceProperties( &c->prop, device ) );
+  CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+  CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) );
+  CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) );
+  CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<128, 128, 64, 32, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
+  CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<64, 64, 32, 32, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM ) );
+  CKN( cudaFuncSetAttribute( potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM ) );
+  CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
+  CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
+  memset( &c->stats, 0, sizeof( c->stats ) );
+  return c;
+}
+
+static void release_symbolic( b200_ctx* c ) {
+  cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
+  c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
+  c->amap.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
+  c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
+  c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release();
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dB ); cudaFree( c->dX );
+  c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
+  c->launches.clear(); c->slaunches.clear();
+  c->factored = false; c->device_bytes = 0;
+}
+
+extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
+  if ( !c ) return;
+  cudaSetDevice( c->device );
+  cudaStreamSynchronize( c->stream );
+  release_symbolic( c );
+  cudaFree( c->dErr ); cudaFree( c->dPert ); if ( c->flush_buf ) cudaFree( c->flush_buf );
+  cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 );
+  cudaStreamDestroy( c->stream );
+  delete c;
+}
+
+/* ------------------------------------------------- schedule construction */
+static void add_gemm( std::vector<GemmTask>& tasks, std::vector<Tile>& big, std::vector<Tile>& small, double& flops,
+                      double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N, int K, int lower, int diag ) {
+  if ( M <= 0 || N <= 0 || K <= 0 ) return;
+  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = ldc; t.lda = lda; t.ldb = ldb; t.M = M; t.N = N; t.K = K; t.lower = lower; t.diag = diag;
+  const int id = ( int )tasks.size();
+  tasks.push_back( t );
+  const bool isbig = ( M > 96 && N > 96 ) || ( ( int64_t )M * N > 64 * 64 * 6 && M > 64 && N > 32 );
+  const int bm = isbig ? 128 : 64, bn = isbig ? 128 : 64;
+  std::vector<Tile>& tl = isbig ? big : small;
+  for ( int tn = 0; tn * bn < N; tn++ )
+    for ( int tm = 0; tm * bm < M; tm++ ) {
+      if ( lower ) { /* skip tiles strictly above the stored triangle: max row + diag < min col */
+        const int rmax = std::min( M, ( tm + 1 ) * bm ) - 1, cmin = tn * bn;
+        if ( rmax + diag < cmin ) continue;
+      }
+      Tile x; x.task = id; x.tm = ( unsigned short )tm; x.tn = ( unsigned short )tn; tl.push_back( x );
+      const int mm = std::min( bm, M - tm * bm ), nn = std::min( bn, N - tn * bn );
+      flops += 2.0 * mm * nn * K;
+    }
+}
+
+extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
+  if ( !c || !S ) return B200_ERR_ARG;
+  CK( cudaSetDevice( c->device ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  release_symbolic( c );
+  const int ns = S->ns, n = S->n;
+  const bool LU = S->kind == B200_KIND_LU;
+  c->n = n; c->ns = ns; c->kind = S->kind; c->maxdepth = S->maxdepth; c->nnzA = S->nnzA;
+  c->lsize = S->stored_nnzL; c->cb_arena[0] = S->cb_arena[0]; c->cb_arena[1] = S->cb_arena[1];
+  c->flops_exact = S->flops * ( LU ? 2.0 : 1.0 ); c->flops_stored = S->stored_flops * ( LU ? 2.0 : 1.0 );
+
+  /* ---- per-supernode metadata, children lists, level lists */
+  std::vector<SnMeta> meta( ns );
+  std::vector<int> child_cnt( ns + 1, 0 ), child_list;
+  for ( int s = 0; s < ns; s++ ) if ( S->sn_parent[s] >= 0 ) child_cnt[S->sn_parent[s] + 1]++;
+  for ( int s = 0; s < ns; s++ ) child_cnt[s + 1] += child_cnt[s];
+  child_list.resize( child_cnt[ns] );
+  { std::vector<int> w( child_cnt.begin(), child_cnt.end() - 1 ); for ( int s = 0; s < ns; s++ ) if ( S->sn_parent[s] >= 0 ) child_list[w[S->sn_parent[s]]++] = s; }
+  std::vector<std::vector<int>> levels( S->maxdepth + 1 );
+  c->level_cb.assign( S->maxdepth + 1, 0 ); c->level_w.assign( S->maxdepth + 1, 0 );
+  int64_t invoff = 0;
+  for ( int s = 0; s < ns; s++ ) {
+    SnMeta& m = meta[s];
+    m.lptr = S->lptr[s]; m.uptr = S->uptr[s]; m.cbptr = S->cbptr[s]; m.rowptr = S->rowptr[s];
+    m.c0 = S->sn_start[s]; m.k = S->sn_start[s + 1] - S->sn_start[s]; m.f = ( int )( S->rowptr[s + 1] - S->rowptr[s] );
+    m.parent = S->sn_parent[s]; m.depth = S->sn_depth[s]; m.child_begin = child_cnt[s]; m.child_end = child_cnt[s + 1]; m.pad = 0;
+    m.invptr = invoff; invoff += ( int64_t )( m.k / NB ) * NB * NB + ( int64_t )( m.k % NB ) * ( m.k % NB );
+    const int d = m.depth; const int64_t u = m.f - m.k;
+    levels[d].push_back( s );
+    c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u * u + 1 ) & ~( int64_t )1 ) );
+    m.wptr = c->level_w[d]; c->level_w[d] += u;
+  }
+  c->invsize = invoff;
+  c->w_rows[0] = c->w_rows[1] = 0;
+  for ( int d = 0; d <= S->maxdepth; d++ ) c->w_rows[d & 1] = std::max( c->w_rows[d & 1], c->level_w[d] );
+
+  /* ---- device storage */
+  size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
+  const double need = ( double )c->lsize * 8.0 * ( LU ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 2 : 1 ) + ( double )S->nnzA * 16.0;
+  if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
+  CK( cudaMalloc( &c->dL, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
+  if ( LU ) CK( cudaMalloc( &c->dU, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
+  for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dCB[a], std::max<int64_t>( c->cb_arena[a], 2 ) * 8 ) );
+  CK( cudaMalloc( &c->dInv, std::max<int64_t>( invoff, 1 ) * 8 ) );
+  if ( LU ) { CK( cudaMalloc( &c->dInv2, std::max<int64_t>( invoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
+  CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
+  c->device_bytes = ( int64_t )need;
+  { std::vector<int64_t> v( S->amap, S->amap + S->nnzA ); if ( c->amap.upload( v ) ) return B200_ERR_CUDA; }
+  { std::vector<int> v( S->perm, S->perm + n ); if ( c->perm.upload( v ) ) return B200_ERR_CUDA; }
+  { std::vector<int> v( S->rowidx, S->rowidx + S->rowptr[ns] ); if ( c->rowidx.upload( v ) ) return B200_ERR_CUDA; }
+  { std::vector<int> v( S->relidx, S->relidx + S->rowptr[ns] ); if ( c->relidx.upload( v ) ) return B200_ERR_CUDA; }
+  if ( c->child_list.upload( child_list ) ) return B200_ERR_CUDA;
+  if ( c->sn.upload( meta ) ) return B200_ERR_CUDA;
+
+  /* ---- factor schedule */
+  std::vector<GemmTask> gt; std::vector<Tile> tb, ts; std::vector<DiagTask> dt; std::vector<TrsmTask> tt; std::vector<RowTile> ttl; std::vector<AsmTask> at;
+  std::vector<Launch>& LS = c->launches;
+  double* Lb = c->dL; double* Ub = c->dU;
+  for ( int d = S->maxdepth; d >= 0; d-- ) {
+    const std::vector<int>& lv = levels[d];
+    double* CB = c->dCB[d & 1];
+    if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, d & 1, c->level_cb[d], d, 0.0 } );
+    { /* extend-add of the children (they live at depth d+1) */
+      const int64_t first = ( int64_t )at.size();
+      for ( int s : lv ) {
+        if ( meta[s].child_begin == meta[s].child_end ) continue;
+        bool any = false;
+        for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
+        if ( !any ) continue;
+        for ( int c0 = 0; c0 < meta[s].f; c0 += ASM_COLS ) at.push_back( { s, c0, std::min( ASM_COLS, meta[s].f - c0 ) } );
+      }
+      if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
+    }
+    int maxk = 0;
+    for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
+    for ( int J = 0; J < maxk; J += NBO ) {
+      for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
+        const int64_t d0 = ( int64_t )dt.size();
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( j0 >= m.k ) continue;
+          const int nb = std::min( NB, m.k - j0 );
+          DiagTask x; x.lda = m.f; x.nb = nb; x.col = m.c0 + j0;
+          x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.f; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.f : nullptr;
+          x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+          x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
+          dt.push_back( x );
+        }
+        if ( ( int64_t )dt.size() == d0 ) break;
+        LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
+        /* rows below the diagonal block */
+        const int64_t t0 = ( int64_t )tt.size(), tl0 = ( int64_t )ttl.size();
+        double tflops = 0;
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( j0 >= m.k ) continue;
+          const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
+          if ( below <= 0 ) continue;
+          const double* inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB;
+          const double* inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+          TrsmTask x; x.B = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.f; x.ldb = m.f; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr;
+          int id = ( int )tt.size(); tt.push_back( x );
+          for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
+          tflops += ( double )below * nb * nb;
+          if ( LU ) {
+            TrsmTask y; y.B = Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.f; y.ldb = m.f; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0;
+            id = ( int )tt.size(); tt.push_back( y );
+            for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
+            tflops += ( double )below * nb * nb;
+          }
+        }
+        if ( ( int64_t )ttl.size() > tl0 ) LS.push_back( { LK_TRSM, tl0, ( int64_t )ttl.size() - tl0, d, tflops } );
+        ( void )t0;
+        /* update of the remaining columns of this outer panel */
+        const int64_t b0 = ( int64_t )tb.size(), s0 = ( int64_t )ts.size();
+        double fb = 0, fs = 0;
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( j0 >= m.k ) continue;
+          const int nb = std::min( NB, m.k - j0 ); const int jn = j0 + nb; const int jend = std::min( m.k, J + NBO );
+          if ( jn >= jend ) continue;
+          double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+          double fl = 0;
+          if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, 0 );
+          else {
+            add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, Up + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, 0 );
+            add_gemm( gt, tb, ts, fl, Up + jn + ( int64_t )jn * m.f, m.f, Up + jn + ( int64_t )j0 * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, -1 );
+          }
+          fb += fl;
+        }
+        ( void )fs;
+        if ( ( int64_t )tb.size() > b0 ) LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } );
+        if ( ( int64_t )ts.size() > s0 ) LS.push_back( { LK_GEMM_SMALL, s0, ( int64_t )ts.size() - s0, d, 0.0 } );
+        if ( !LS.empty() && ( LS.back().kind == LK_GEMM_BIG || LS.back().kind == LK_GEMM_SMALL ) ) LS.back().flops += fb;
+      }
+      /* trailing update with the whole outer panel: remaining pivot columns and the contribution block */
+      const int64_t b0 = ( int64_t )tb.size(), s0 = ( int64_t )ts.size();
+      double fl = 0;
+      for ( int s : lv ) {
+        const SnMeta& m = meta[s];
+        if ( J >= m.k ) continue;
+        const int kb = std::min( NBO, m.k - J ); const int Jn = J + kb; const int u = m.f - m.k;
+        double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+        double* cb = CB + m.cbptr;
+        if ( !LU ) {
+          if ( Jn < m.k ) add_gemm( gt, tb, ts, fl, Lp + Jn + ( int64_t )Jn * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, 0 );
+          if ( u > 0 ) add_gemm( gt, tb, ts, fl, cb, u, Lp + m.k + ( int64_t )J * m.f, m.f, Lp + m.k + ( int64_t )J * m.f, m.f, u, u, kb, 1, 0 );
+        } else {
+          if ( Jn < m.k ) {
+            add_gemm( gt, tb, ts, fl, Lp + Jn + ( int64_t )Jn * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, Up + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, 0 );
+            add_gemm( gt, tb, ts, fl, Up + Jn + ( int64_t )Jn * m.f, m.f, Up + Jn + ( int64_t )J * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, -1 );
+          }
+          if ( u > 0 ) add_gemm( gt, tb, ts, fl, cb, u, Lp + m.k + ( int64_t )J * m.f, m.f, Up + m.k + ( int64_t )J * m.f, m.f, u, u, kb, 0, 0 );
+        }
+      }
+      if ( ( int64_t )tb.size() > b0 ) LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } );
+      if ( ( int64_t )ts.size() > s0 ) LS.push_back( { LK_GEMM_SMALL, s0, ( int64_t )ts.size() - s0, d, 0.0 } );
+      if ( !LS.empty() && ( LS.back().kind == LK_GEMM_BIG || LS.back().kind == LK_GEMM_SMALL ) ) LS.back().flops += fl;
+    }
+  }
+  if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
+       c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
+
+  /* ---- solve schedule: forward deepest->root, backward root->deepest */
+  std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<int> gp;
+  std::vector<SLaunch>& SS = c->slaunches;
+  c->max_partial_tiles = 0;
+  for ( int d = S->maxdepth; d >= 0; d-- ) {
+    const std::vector<int>& lv = levels[d];
+    if ( c->level_w[d] > 0 ) SS.push_back( { SK_FWD_ZERO_W, d & 1, c->level_w[d], 0, 0, d } );
+    { const int64_t g0 = ( int64_t )gp.size();
+      for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } } if ( any ) gp.push_back( s ); }
+      if ( ( int64_t )gp.size() > g0 ) SS.push_back( { SK_FWD_GATHER, g0, ( int64_t )gp.size() - g0, 0, 0, d } ); }
+    int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
+    for ( int j0 = 0; j0 < maxk; j0 += NB ) {
+      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size();
+      for ( int s : lv ) {
+        const SnMeta& m = meta[s]; if ( j0 >= m.k ) continue;
+        const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
+        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.first_partial = 0; x.ntiles = 0; x.pad = 0;
+        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
+        for ( int r0 = 0; r0 < below; r0 += 256 ) ft.push_back( { id, r0 } );
+      }
+      SS.push_back( { SK_FWD_DIAG, b0, ( int64_t )sb.size() - b0, 0, 0, d } );
+      if ( ( int64_t )ft.size() > t0 ) SS.push_back( { SK_FWD_UPDATE, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } );
+    }
+  }
+  for ( int d = 0; d <= S->maxdepth; d++ ) {
+    const std::vector<int>& lv = levels[d];
+    int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
+    const int nblk = ( maxk + NB - 1 ) / NB;
+    for ( int bi = nblk - 1; bi >= 0; bi-- ) {
+      const int j0 = bi * NB;
+      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )bt.size();
+      int64_t np = 0;
+      for ( int s : lv ) {
+        const SnMeta& m = meta[s]; if ( j0 >= m.k ) continue;
+        const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
+        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.first_partial = ( int )np; x.ntiles = ( below + BWD_ROWS - 1 ) / BWD_ROWS; x.pad = 0;
+        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
+        for ( int r0 = 0; r0 < below; r0 += BWD_ROWS ) bt.push_back( { id, r0 } );
+        np += x.ntiles;
+      }
+      c->max_partial_tiles = std::max( c->max_partial_tiles, np );
+      if ( ( int64_t )bt.size() > t0 ) SS.push_back( { SK_BWD_PARTIAL, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )bt.size() - t0, d } );
+      SS.push_back( { SK_BWD_DIAG, b0, ( int64_t )sb.size() - b0, 0, 0, d } );
+    }
+  }
+  if ( c->sblk.upload( sb ) || c->fwd_tiles.upload( ft ) || c->bwd_tiles.upload( bt ) || c->gather_parents.upload( gp ) ) return B200_ERR_CUDA;
+  c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
+                     c->asm_tasks.bytes() + c->sblk.bytes() + c->fwd_tiles.bytes() + c->bwd_tiles.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
+  CK( cudaStreamSynchronize( c->stream ) );
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------- factor */
+static int run_factor( b200_ctx* c ) {
+  const bool LU = c->kind == B200_KIND_LU;
+  cudaStream_t st = c->stream;
+  CK( cudaEventRecord( c->ev0, st ) );
+  CK( cudaMemsetAsync( c->dErr, 0, sizeof( int ), st ) );
+  CK( cudaMemsetAsync( c->dPert, 0, sizeof( int ), st ) );
+  CK( cudaMemsetAsync( c->dL, 0, ( size_t )c->lsize * 8, st ) );
+  if ( LU ) CK( cudaMemsetAsync( c->dU, 0, ( size_t )c->lsize * 8, st ) );
+  if ( c->nnzA > 0 ) {
+    const int blocks = ( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 16 );
+    scatter_A_kernel<<<blocks, 256, 0, st>>>( c->dVals, c->amap.d, c->nnzA, c->dL, c->dU );
+  }
+  int64_t nlaunch = 3 + ( LU ? 1 : 0 );
+  double gemm_flops = 0; int64_t gemm_launches = 0;
+  for ( int k = 0; k < LK_COUNT; k++ ) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+  for ( const Launch& l : c->launches ) {
+    if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
+    switch ( l.kind ) {
+      case LK_MEMSET_CB: CK( cudaMemsetAsync( c->dCB[l.first], 0, ( size_t )l.count * 8, st ) ); break;
+      case LK_ASM:
+        if ( LU ) extend_add_kernel<true><<<( unsigned )l.count, 256, 0, st>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
+        else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, st>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
+        break;
+      case LK_DIAG:
+        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, st>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
+        else potrf_diag_kernel<<<( unsigned )l.count, 256, POTRF_SMEM, st>>>( c->diag_tasks.d + l.first, c->dErr );
+        break;
+      case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, st>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
+      case LK_GEMM_BIG:
+        gemm_nt_dmma_kernel<128, 128, 64, 32, GEMM_STAGES><<<( unsigned )l.count, 256, BIG_SMEM, st>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
+        gemm_flops += l.flops; gemm_launches++; break;
+      case LK_GEMM_SMALL:
+        gemm_nt_dmma_kernel<64, 64, 32, 32, GEMM_STAGES><<<( unsigned )l.count, 128, SMALL_SMEM, st>>>( c->gemm_tasks.d, c->tiles_small.d + l.first );
+        gemm_flops += l.flops; gemm_launches++; break;
+    }
+    nlaunch++;
+    if ( c->profile ) {
+      CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) );
+      float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->prof_ms[l.kind] += ms; c->prof_n[l.kind]++;
+    }
+  }
+  CK( cudaEventRecord( c->ev1, st ) );
+  CK( cudaGetLastError() );
+  int err = 0, pert = 0;
+  CK( cudaMemcpyAsync( &err, c->dErr, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  CK( cudaMemcpyAsync( &pert, c->dPert, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  CK( cudaStreamSynchronize( st ) );
+  float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
+  c->stats.factor_ms = ms; c->stats.launches = nlaunch; c->stats.gemm_flops = gemm_flops; c->stats.gemm_launches = gemm_launches;
+  c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] + c->prof_ms[LK_GEMM_SMALL] : 0.0;
+  c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes;
+  if ( err != 0 ) { char a[64]; snprintf( a, 64, "%d", err - 1 ); set_err( "matrix is not positive definite (pivot column %s of the permuted matrix)%s", a, "" ); c->factored = false; return B200_ERR_NOT_SPD; }
+  c->factored = true;
+  return B200_OK;
+}
+
+extern "C" int b200_factor_device( b200_ctx_t* c, const double* d_vals ) {
+  if ( !c || !c->dL ) return B200_ERR_STATE;
+  CK( cudaSetDevice( c->device ) );
+  if ( d_vals != c->dVals && c->nnzA > 0 ) CK( cudaMemcpyAsync( c->dVals, d_vals, ( size_t )c->nnzA * 8, cudaMemcpyDeviceToDevice, c->stream ) );
+  if ( c->kind == B200_KIND_LU && c->tiny == 0.0 ) c->tiny = 1.5e-8;
+  c->stats.h2d_ms = 0;
+  return run_factor( c );
+}
+
+extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
+  if ( !c || !c->dL ) return B200_ERR_STATE;
+  CK( cudaSetDevice( c->device ) );
+  if ( c->kind == B200_KIND_LU ) { /* static-pivot threshold: sqrt(eps) * max|a_ij| */
+    double mx = 0; for ( int64_t e = 0; e < c->nnzA; e++ ) mx = std::max( mx, std::fabs( vals[e] ) );
+    c->tiny = 1.5e-8 * ( mx > 0 ? mx : 1.0 );
+  }
+  CK( cudaEventRecord( c->evp0, c->stream ) );
+  if ( c->nnzA > 0 ) CK( cudaMemcpyAsync( c->dVals, vals, ( size_t )c->nnzA * 8, cudaMemcpyHostToDevice, c->stream ) );
+  CK( cudaEventRecord( c->evp1, c->stream ) );
+  int r = run_factor( c );
+  float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->stats.h2d_ms = ms;
+  return r;
+}
+
+/* -------------------------------------------------------------- solve */
+static int ensure_solve_ws( b200_ctx* c, int p ) {
+  if ( p <= c->solve_p_cap ) return B200_OK;
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial );
+  c->dY = c->dW[0] = c->dW[1] = c->dPartial = nullptr; c->solve_p_cap = 0;
+  CK( cudaMalloc( &c->dY, ( size_t )c->n * p * 8 ) );
+  for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dW[a], ( size_t )std::max<int64_t>( c->w_rows[a], 1 ) * p * 8 ) );
+  const int pchunks = ( p + PC - 1 ) / PC;
+  CK( cudaMalloc( &c->dPartial, ( size_t )std::max<int64_t>( c->max_partial_tiles, 1 ) * pchunks * NB * PC * 8 ) );
+  c->solve_p_cap = p;
+  return B200_OK;
+}
+
+static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
+  const bool LU = c->kind == B200_KIND_LU;
+  cudaStream_t st = c->stream;
+  const int n = c->n;
+  int r = ensure_solve_ws( c, p ); if ( r ) return r;
+  const int pchunks = ( p + PC - 1 ) / PC;
+  const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * p + 255 ) / 256, 148 * 32 );
+  CK( cudaEventRecord( c->ev0, st ) );
+  permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, c->dY );
+  int64_t nl = 2;
+  const int64_t ldw[2] = { std::max<int64_t>( c->w_rows[0], 1 ), std::max<int64_t>( c->w_rows[1], 1 ) };
+  for ( const SLaunch& l : c->slaunches ) {
+    const int a = l.depth & 1, ac = ( l.depth + 1 ) & 1;
+    switch ( l.kind ) {
+      case SK_FWD_ZERO_W:
+        CK( cudaMemset2DAsync( c->dW[a], ( size_t )ldw[a] * 8, 0, ( size_t )l.count * 8, ( size_t )p, st ) );
+        break;
+      case SK_FWD_GATHER:
+        fwd_gather_kernel<<<dim3( ( unsigned )l.count, pchunks ), 256, 0, st>>>( c->gather_parents.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, n, p, c->dW[a], ldw[a], c->dW[ac], ldw[ac] );
+        break;
+      case SK_FWD_DIAG:
+        fwd_diag_kernel<<<dim3( ( unsigned )l.count, pchunks ), 64, 0, st>>>( c->sblk.d + l.first, c->sn.d, c->dInv, LU ? c->dPiv : nullptr, c->dY, n, p );
+        break;
+      case SK_FWD_UPDATE:
+        fwd_update_kernel<<<dim3( ( unsigned )l.ntiles, pchunks ), 256, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dY, n, p, c->dW[a], ldw[a] );
+        break;
+      case SK_BWD_PARTIAL:
+        if ( LU ) bwd_partial_kernel<true><<<dim3( ( unsigned )l.ntiles, pchunks ), 256, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dU, c->rowidx.d, c->dY, n, p, c->dPartial );
+        else bwd_partial_kernel<false><<<dim3( ( unsigned )l.ntiles, pchunks ), 256, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dU, c->rowidx.d, c->dY, n, p, c->dPartial );
+        break;
+      case SK_BWD_DIAG:
+        bwd_diag_kernel<<<dim3( ( unsigned )l.count, pchunks ), 64, 0, st>>>( c->sblk.d + l.first, c->sn.d, LU ? c->dInv2 : c->dInv, c->dY, n, p, c->dPartial );
+        break;
+    }
+    nl++;
+  }
+  permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dY, c->perm.d, n, p, d_x );
+  CK( cudaEventRecord( c->ev1, st ) );
+  CK( cudaGetLastError() );
+  CK( cudaStreamSynchronize( st ) );
+  float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
+  c->stats.solve_ms = ms; c->stats.solve_launches = nl;
+  return B200_OK;
+}
+
+extern "C" int b200_solve_device( b200_ctx_t* c, const double* d_b, int p, double* d_x ) {
+  if ( !c || !c->factored ) { set_err( "solve before a successful factor%s", "" ); return B200_ERR_STATE; }
+  if ( p <= 0 ) return B200_ERR_ARG;
+  CK( cudaSetDevice( c->device ) );
+  return run_solve( c, d_b, p, d_x );
+}
+
+extern "C" int b200_solve_host( b200_ctx_t* c, const double* b, int p, double* x ) {
+  if ( !c || !c->factored ) { set_err( "solve before a successful factor%s", "" ); return B200_ERR_STATE; }
+  if ( p <= 0 || !b || !x ) return B200_ERR_ARG;
+  CK( cudaSetDevice( c->device ) );
+  if ( p > c->io_p_cap ) {
+    cudaFree( c->dB ); cudaFree( c->dX ); c->dB = c->dX = nullptr; c->io_p_cap = 0;
+    CK( cudaMalloc( &c->dB, ( size_t )c->n * p * 8 ) ); CK( cudaMalloc( &c->dX, ( size_t )c->n * p * 8 ) );
+    c->io_p_cap = p;
+  }
+  const size_t bytes = ( size_t )c->n * p * 8;
+  CK( cudaEventRecord( c->evp0, c->stream ) );
+  CK( cudaMemcpyAsync( c->dB, b, bytes, cudaMemcpyHostToDevice, c->stream ) );
+  CK( cudaEventRecord( c->evp1, c->stream ) );
+  int r = run_solve( c, c->dB, p, c->dX );
+  if ( r ) return r;
+  float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->stats.h2d_ms = ms;
+  CK( cudaEventRecord( c->evp0, c->stream ) );
+  CK( cudaMemcpyAsync( x, c->dX, bytes, cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaEventRecord( c->evp1, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->stats.d2h_ms = ms;
+  return B200_OK;
+}
+
+/* ------------------------------------------------------------ helpers */
+extern "C" void* b200_dev_alloc( b200_ctx_t* c, size_t bytes ) { if ( !c ) return nullptr; cudaSetDevice( c->device ); void* p = nullptr; if ( cudaMalloc( &p, bytes ? bytes : 8 ) != cudaSuccess ) { set_err( "cudaMalloc failed%s", "" ); return nullptr; } return p; }
+extern "C" void b200_dev_free( b200_ctx_t* c, void* p ) { if ( c && p ) { cudaSetDevice( c->device ); cudaFree( p ); } }
+extern "C" int b200_dev_upload( b200_ctx_t* c, void* dst, const void* src, size_t bytes ) { if ( !c ) return B200_ERR_ARG; CK( cudaSetDevice( c->device ) ); CK( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyHostToDevice, c->stream ) ); CK( cudaStreamSynchronize( c->stream ) ); return B200_OK; }
+extern "C" int b200_dev_download( b200_ctx_t* c, void* dst, const void* src, size_t bytes ) { if ( !c ) return B200_ERR_ARG; CK( cudaSetDevice( c->device ) ); CK( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToHost, c->stream ) ); CK( cudaStreamSynchronize( c->stream ) ); return B200_OK; }
+extern "C" void* b200_host_alloc_pinned( size_t bytes ) { void* p = nullptr; if ( cudaHostAlloc( &p, bytes ? bytes : 8, cudaHostAllocDefault ) != cudaSuccess ) return nullptr; return p; }
+extern "C" void b200_host_free_pinned( void* p ) { if ( p ) cudaFreeHost( p ); }
+extern "C" int b200_dev_sync( b200_ctx_t* c ) { if ( !c ) return B200_ERR_ARG; CK( cudaSetDevice( c->device ) ); CK( cudaStreamSynchronize( c->stream ) ); return B200_OK; }
+extern "C" int b200_flush_l2( b200_ctx_t* c ) {
+  if ( !c ) return B200_ERR_ARG;
+  CK( cudaSetDevice( c->device ) );
+  if ( !c->flush_buf ) { c->flush_bytes = ( size_t )256 << 20; CK( cudaMalloc( &c->flush_buf, c->flush_bytes ) ); }
+  CK( cudaMemsetAsync( c->flush_buf, 1, c->flush_bytes, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  return B200_OK;
+}
+extern "C" int b200_get_stats( b200_ctx_t* c, b200_stats_t* out ) { if ( !c || !out ) return B200_ERR_ARG; *out = c->stats; return B200_OK; }
+extern "C" int b200_set_profile( b200_ctx_t* c, int on ) { if ( !c ) return B200_ERR_ARG; c->profile = on != 0; return B200_OK; }
+extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
+  if ( !c || !buf || len == 0 ) return B200_ERR_ARG;
+  std::string s;
+  char line[256];
+  for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
+  snprintf( buf, len, "%s", s.c_str() );
+  return B200_OK;
+}
+
+/* diagnostics: copy a range of a device array to the host. which: 0 = L panels, 1 = U' panels, 2 = inverse blocks */
+extern "C" int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count ) {
+  if ( !c || !dst ) return B200_ERR_ARG;
+  CK( cudaSetDevice( c->device ) );
+  const double* src = which == 0 ? c->dL : which == 1 ? c->dU : c->dInv;
+  if ( !src ) return B200_ERR_STATE;
+  CK( cudaMemcpy( dst, src + offset, ( size_t )count * 8, cudaMemcpyDeviceToHost ) );
+  return B200_OK;
+}
+
+/* ---- micro-benchmarks: the FP64 roof of OUR kernel and the HBM copy roof */
+extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ) {
+  if ( !c || m <= 0 || n <= 0 || k <= 0 ) return -1.0;
+  cudaSetDevice( c->device );
+  double *A, *B, *C;
+  if ( cudaMalloc( &A, ( size_t )m * k * 8 ) || cudaMalloc( &B, ( size_t )n * k * 8 ) || cudaMalloc( &C, ( size_t )m * n * 8 ) ) return -1.0;
+  cudaMemset( A, 0, ( size_t )m * k * 8 ); cudaMemset( B, 0, ( size_t )n * k * 8 ); cudaMemset( C, 0, ( size_t )m * n * 8 );
+  std::vector<GemmTask> gt; std::vector<Tile> tb, ts; double fl = 0;
+  add_gemm( gt, tb, ts, fl, C, m, A, m, B, n, m, n, k, 0, 0 );
+  DevVec<GemmTask> dgt; DevVec<Tile> dtb, dts; dgt.upload( gt ); dtb.upload( tb ); dts.upload( ts );
+  float best = 1e30f;
+  for ( int it = 0; it < iters + 2; it++ ) {
+    cudaEventRecord( c->ev0, c->stream );
+    if ( dtb.n ) gemm_nt_dmma_kernel<128, 128, 64, 32, GEMM_STAGES><<<( unsigned )dtb.n, 256, BIG_SMEM, c->stream>>>( dgt.d, dtb.d );
+    if ( dts.n ) gemm_nt_dmma_kernel<64, 64, 32, 32, GEMM_STAGES><<<( unsigned )dts.n, 128, SMALL_SMEM, c->stream>>>( dgt.d, dts.d );
+    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
+    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
+  }
+  dgt.release(); dtb.release(); dts.release(); cudaFree( A ); cudaFree( B ); cudaFree( C );
+  if ( cudaGetLastError() != cudaSuccess ) return -1.0;
+  return 2.0 * m * n * ( double )k / ( best * 1e-3 ) / 1e12;
+}
+
+extern "C" double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters ) {
+  if ( !c ) return -1.0;
+  cudaSetDevice( c->device );
+  double2 *a, *b; bytes &= ~( size_t )15;
+  if ( cudaMalloc( &a, bytes ) || cudaMalloc( &b, bytes ) ) return -1.0;
+  cudaMemset( a, 0, bytes );
+  float best = 1e30f;
+  for ( int it = 0; it < iters + 2; it++ ) {
+    cudaEventRecord( c->ev0, c->stream );
+    stream_copy_kernel<<<148 * 16, 512, 0, c->stream>>>( a, b, ( int64_t )( bytes / 16 ) );
+    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
+    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
+  }
+  cudaFree( a ); cudaFree( b );
+  return 2.0 * bytes / ( best * 1e-3 ) / 1e9;
+}
