@@ -92,6 +92,9 @@ typedef struct b200_symbolic {
   int maxdepth;          /* deepest level                                          */
   int64_t cb_arena[2];   /* doubles needed by the two contribution-block arenas    */
   int64_t* cbptr;        /* [ns] offset of the contribution block in its arena     */
+  int64_t* spmv_ptr;     /* [n+1] row pointers of the FULL matrix in the original numbering  */
+  int* spmv_col;         /* column of each entry                                              */
+  int* spmv_src;         /* index of its value in the input array (residual for refinement)   */
   double t_order, t_symbolic;  /* seconds spent in ordering / rest of the analysis */
 } b200_symbolic_t;
 
@@ -136,6 +139,10 @@ void* b200_host_alloc_pinned( size_t bytes );
 void b200_host_free_pinned( void* p );
 int b200_dev_sync( b200_ctx_t* c );
 int b200_flush_l2( b200_ctx_t* c );             /* write a >L2 buffer between timed steps */
+
+/* iterative refinement steps per solve (default 1): r = b - A x is accumulated in
+ * double-double on the device, then one more pair of sweeps corrects x */
+int b200_set_refinement( b200_ctx_t* c, int steps );
 
 /* statistics of the last factor / solve (device-event milliseconds) */
 typedef struct b200_stats {

@@ -53,7 +53,8 @@ class b200_symbolic_t(C.Structure):
                 ("rowptr", C.POINTER(C.c_int64)), ("rowidx", C.POINTER(C.c_int)), ("relidx", C.POINTER(C.c_int)),
                 ("lptr", C.POINTER(C.c_int64)), ("uptr", C.POINTER(C.c_int64)), ("amap", C.POINTER(C.c_int64)),
                 ("stored_nnzL", C.c_int64), ("stored_flops", C.c_double), ("maxfront", C.c_int), ("maxdepth", C.c_int),
-                ("cb_arena", C.c_int64 * 2), ("cbptr", C.POINTER(C.c_int64)), ("t_order", C.c_double), ("t_symbolic", C.c_double)]
+                ("cb_arena", C.c_int64 * 2), ("cbptr", C.POINTER(C.c_int64)),
+                ("spmv_ptr", C.POINTER(C.c_int64)), ("spmv_col", C.POINTER(C.c_int)), ("spmv_src", C.POINTER(C.c_int)), ("t_order", C.c_double), ("t_symbolic", C.c_double)]
 
 
 class b200_stats_t(C.Structure):
@@ -79,7 +80,7 @@ EXPORTED_SYMBOLS = [
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_upload_symbolic", "b200_factor_host", "b200_factor_device",
     "b200_solve_host", "b200_solve_device", "b200_dev_alloc", "b200_dev_free", "b200_dev_upload", "b200_dev_download",
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
-    "b200_get_profile", "b200_debug_read", "b200_bench_dgemm_tflops", "b200_bench_stream_gbs",
+    "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_stream_gbs",
 ]
 
 _lib = None
@@ -148,6 +149,7 @@ def lib():
     L.b200_get_stats.argtypes = [vp, C.POINTER(b200_stats_t)]
     L.b200_set_profile.argtypes = [vp, i32]
     L.b200_get_profile.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.b200_set_refinement.argtypes = [vp, i32]
     L.b200_debug_read.argtypes = [vp, i32, vp, i64, i64]
     L.b200_bench_dgemm_tflops.restype = dbl; L.b200_bench_dgemm_tflops.argtypes = [vp, i32, i32, i32, i32]
     L.b200_bench_stream_gbs.restype = dbl; L.b200_bench_stream_gbs.argtypes = [vp, C.c_size_t, i32]

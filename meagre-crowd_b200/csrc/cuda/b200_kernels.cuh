@@ -614,6 +614,35 @@ __global__ void __launch_bounds__( 64 ) bwd_diag_kernel( const SolveBlk* __restr
   }
 }
 
+/* residual r = b - A x with the sum carried in double-double (error-free products through
+ * fma, Knuth two-sum), so that one refinement step recovers x to working accuracy */
+__global__ void residual_dd_kernel( const int64_t* __restrict__ rp, const int* __restrict__ col, const int* __restrict__ src,
+                                    const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ b,
+                                    int n, int p, double* __restrict__ r ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < tot; e += stride ) {
+    const int i = ( int )( e % n ); const int64_t c = e / n;
+    const double* xc = x + c * n;
+    double hi = b[e], lo = 0.0;
+    for ( int64_t q = rp[i]; q < rp[i + 1]; q++ ) {
+      const double a = vals[src[q]], xv = xc[col[q]];
+      const double pr = -a * xv;
+      const double pe = fma( -a, xv, -pr );        /* exact: -a*xv = pr + pe */
+      const double s = hi + pr;
+      const double bb = s - hi;
+      const double se = ( hi - ( s - bb ) ) + ( pr - bb );
+      hi = s; lo += se + pe;
+    }
+    r[e] = hi + lo;
+  }
+}
+__global__ void axpy_kernel( double* __restrict__ x, const double* __restrict__ d, int64_t tot ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < tot; e += stride ) x[e] += d[e];
+}
+
 /* micro-benchmark: plain streaming copy */
 __global__ void stream_copy_kernel( const double2* __restrict__ a, double2* __restrict__ b, int64_t n2 ) {
   int64_t i = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;

@@ -77,7 +77,9 @@ struct b200_ctx {
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
   int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr;
-  DevVec<int64_t> amap; DevVec<int> perm, rowidx, relidx, child_list;
+  DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
+  int refine = 1;
+  double *dR = nullptr, *dD = nullptr;
   DevVec<SnMeta> sn;
   DevVec<GemmTask> gemm_tasks; DevVec<Tile> tiles_big, tiles_small;
   DevVec<DiagTask> diag_tasks; DevVec<TrsmTask> trsm_tasks; DevVec<RowTile> trsm_tiles;
@@ -124,10 +126,11 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
 static void release_symbolic( b200_ctx* c ) {
   cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
-  c->amap.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
+  c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
   c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
   c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release();
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dB ); cudaFree( c->dX );
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD );
+  c->dR = c->dD = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
   c->launches.clear(); c->slaunches.clear();
   c->factored = false; c->device_bytes = 0;
@@ -217,6 +220,9 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   { std::vector<int> v( S->perm, S->perm + n ); if ( c->perm.upload( v ) ) return B200_ERR_CUDA; }
   { std::vector<int> v( S->rowidx, S->rowidx + S->rowptr[ns] ); if ( c->rowidx.upload( v ) ) return B200_ERR_CUDA; }
   { std::vector<int> v( S->relidx, S->relidx + S->rowptr[ns] ); if ( c->relidx.upload( v ) ) return B200_ERR_CUDA; }
+  { std::vector<int64_t> v( S->spmv_ptr, S->spmv_ptr + n + 1 ); if ( c->spmv_ptr.upload( v ) ) return B200_ERR_CUDA;
+    std::vector<int> a( S->spmv_col, S->spmv_col + S->spmv_ptr[n] ), b( S->spmv_src, S->spmv_src + S->spmv_ptr[n] );
+    if ( c->spmv_col.upload( a ) || c->spmv_src.upload( b ) ) return B200_ERR_CUDA; }
   if ( c->child_list.upload( child_list ) ) return B200_ERR_CUDA;
   if ( c->sn.upload( meta ) ) return B200_ERR_CUDA;
 
@@ -465,9 +471,10 @@ extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
 /* -------------------------------------------------------------- solve */
 static int ensure_solve_ws( b200_ctx* c, int p ) {
   if ( p <= c->solve_p_cap ) return B200_OK;
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial );
-  c->dY = c->dW[0] = c->dW[1] = c->dPartial = nullptr; c->solve_p_cap = 0;
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dR ); cudaFree( c->dD );
+  c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dR = c->dD = nullptr; c->solve_p_cap = 0;
   CK( cudaMalloc( &c->dY, ( size_t )c->n * p * 8 ) );
+  CK( cudaMalloc( &c->dR, ( size_t )c->n * p * 8 ) ); CK( cudaMalloc( &c->dD, ( size_t )c->n * p * 8 ) );
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dW[a], ( size_t )std::max<int64_t>( c->w_rows[a], 1 ) * p * 8 ) );
   const int pchunks = ( p + PC - 1 ) / PC;
   CK( cudaMalloc( &c->dPartial, ( size_t )std::max<int64_t>( c->max_partial_tiles, 1 ) * pchunks * NB * PC * 8 ) );
@@ -475,16 +482,15 @@ static int ensure_solve_ws( b200_ctx* c, int p ) {
   return B200_OK;
 }
 
-static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
+/* one pair of sweeps: d_x = (LL')^-1 d_b  (or (LU)^-1), launches counted into nl */
+static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64_t& nl ) {
   const bool LU = c->kind == B200_KIND_LU;
   cudaStream_t st = c->stream;
   const int n = c->n;
-  int r = ensure_solve_ws( c, p ); if ( r ) return r;
   const int pchunks = ( p + PC - 1 ) / PC;
   const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * p + 255 ) / 256, 148 * 32 );
-  CK( cudaEventRecord( c->ev0, st ) );
   permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, c->dY );
-  int64_t nl = 2;
+  nl += 2;
   const int64_t ldw[2] = { std::max<int64_t>( c->w_rows[0], 1 ), std::max<int64_t>( c->w_rows[1], 1 ) };
   for ( const SLaunch& l : c->slaunches ) {
     const int a = l.depth & 1, ac = ( l.depth + 1 ) & 1;
@@ -512,6 +518,23 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
     nl++;
   }
   permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dY, c->perm.d, n, p, d_x );
+  return B200_OK;
+}
+
+static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
+  cudaStream_t st = c->stream;
+  const int n = c->n;
+  int r = ensure_solve_ws( c, p ); if ( r ) return r;
+  const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * p + 255 ) / 256, 148 * 32 );
+  int64_t nl = 0;
+  CK( cudaEventRecord( c->ev0, st ) );
+  r = sweep_once( c, d_b, p, d_x, nl ); if ( r ) return r;
+  for ( int it = 0; it < c->refine; it++ ) {
+    residual_dd_kernel<<<pblocks, 256, 0, st>>>( c->spmv_ptr.d, c->spmv_col.d, c->spmv_src.d, c->dVals, d_x, d_b, n, p, c->dR );
+    r = sweep_once( c, c->dR, p, c->dD, nl ); if ( r ) return r;
+    axpy_kernel<<<pblocks, 256, 0, st>>>( d_x, c->dD, ( int64_t )n * p );
+    nl += 2;
+  }
   CK( cudaEventRecord( c->ev1, st ) );
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( st ) );
@@ -568,6 +591,7 @@ extern "C" int b200_flush_l2( b200_ctx_t* c ) {
   return B200_OK;
 }
 extern "C" int b200_get_stats( b200_ctx_t* c, b200_stats_t* out ) { if ( !c || !out ) return B200_ERR_ARG; *out = c->stats; return B200_OK; }
+extern "C" int b200_set_refinement( b200_ctx_t* c, int steps ) { if ( !c || steps < 0 ) return B200_ERR_ARG; c->refine = steps; return B200_OK; }
 extern "C" int b200_set_profile( b200_ctx_t* c, int on ) { if ( !c ) return B200_ERR_ARG; c->profile = on != 0; return B200_OK; }
 extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   if ( !c || !buf || len == 0 ) return B200_ERR_ARG;

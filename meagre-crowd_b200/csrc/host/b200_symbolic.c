@@ -36,7 +36,7 @@ void b200_symbolic_free( b200_symbolic_t* S ) {
   free( S->perm ); free( S->iperm ); free( S->parent ); free( S->colcount );
   free( S->sn_start ); free( S->sn_parent ); free( S->sn_depth );
   free( S->rowptr ); free( S->rowidx ); free( S->relidx ); free( S->lptr ); free( S->uptr );
-  free( S->amap ); free( S->cbptr );
+  free( S->amap ); free( S->cbptr ); free( S->spmv_ptr ); free( S->spmv_col ); free( S->spmv_src );
   free( S );
 }
 
@@ -423,6 +423,29 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
     }
   }
   free( col2sn ); free( mark );
+
+  /* ---- 9. row-wise copy of the full pattern (original numbering) for the residual b - A x */
+  {
+    int64_t* rp = calloc( ( size_t )n + 1, sizeof( int64_t ) );
+    for ( int j = 0; j < n; j++ )
+      for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
+        int i = ( int )ri[p];
+        if ( kind == B200_KIND_CHOLESKY ) { if ( i > j ) continue; rp[i + 1]++; if ( i != j ) rp[j + 1]++; }
+        else rp[i + 1]++;
+      }
+    for ( int i = 0; i < n; i++ ) rp[i + 1] += rp[i];
+    int64_t* w = malloc( sizeof( int64_t ) * ( ( size_t )n + 1 ) ); memcpy( w, rp, sizeof( int64_t ) * ( ( size_t )n + 1 ) );
+    S->spmv_col = malloc( sizeof( int ) * ( rp[n] > 0 ? rp[n] : 1 ) ); S->spmv_src = malloc( sizeof( int ) * ( rp[n] > 0 ? rp[n] : 1 ) );
+    for ( int j = 0; j < n; j++ )
+      for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
+        int i = ( int )ri[p];
+        if ( kind == B200_KIND_CHOLESKY && i > j ) continue;
+        int64_t q = w[i]++; S->spmv_col[q] = j; S->spmv_src[q] = ( int )p;
+        if ( kind == B200_KIND_CHOLESKY && i != j ) { q = w[j]++; S->spmv_col[q] = i; S->spmv_src[q] = ( int )p; }
+      }
+    free( w );
+    S->spmv_ptr = rp;
+  }
   S->t_symbolic = now_s() - t1;
   return S;
 }

@@ -11,7 +11,7 @@
  *   - errors: message on stderr + abort(), like the reference's assert()s
  *   - analyze/factorize/evaluate may be repeated on one state (-r N)
  * Tuning comes from the environment because the callbacks carry no options:
- *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_VERBOSE.
+ *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_REFINE (steps, default 1), B200_VERBOSE.
  * There is no CPU fallback: without a usable GPU, init aborts.
  */
 #include <assert.h>
@@ -44,6 +44,8 @@ void solver_init_b200( solver_state_t* s ) {
   const char* dev = getenv( "B200_DEVICE" );
   p->ctx = b200_ctx_create( dev ? atoi( dev ) : 0 );
   if ( p->ctx == NULL ) die( "cannot create a CUDA context (no CPU fallback exists)" );
+  const char* rf = getenv( "B200_REFINE" );
+  if ( rf ) b200_set_refinement( p->ctx, atoi( rf ) );
 }
 
 static void free_expansion( b200_state_t* p ) {

@@ -1,0 +1,237 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (plugin callbacks and shim),
+against the CPU oracle and the reference's golden answer files. Run with -m gpu on a B200.
+
+Tolerances (north_star): x within the reference tests' absolute tolerances on the fixtures
+(5e-14 / 5e-12 / 5e-11, testsuite.at:312-346); scaled backward error
+||Ax-b|| / (||A|| ||x|| + ||b||) <= 1e-12 for SPD systems and for the LU cases here;
+L factors within 1e-12 relative of the oracle's (FP64, different summation order).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import oracle
+from helpers import sym_dict, read_mm_dense, backward_error
+from meagre_crowd_b200 import stencils
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = [("unsym", "default", 5e-14), ("unsym", "rhs1", 5e-14), ("sym", "default", 5e-14), ("sym", "rhs1", 5e-14),
+                ("sym_posdef", "default", 5e-12), ("sym_posdef", "rhs1", 5e-11)]
+
+
+def plugin_solve(mc, A_path, b=None, b_path=None, rep=1):
+    """drive the plugin exactly like main(): load -> solver_init -> solver_solve x rep -> finalize"""
+    L = mc.lib()
+    A = L.malloc_matrix(); assert L.load_matrix(A_path.encode(), A) == 0
+    if b_path:
+        bm = L.malloc_matrix(); assert L.load_matrix(b_path.encode(), bm) == 0
+    else:
+        bm = mc.make_matrix_dcol(np.arange(A.contents.m, dtype=float) if b is None else b)
+    x = L.malloc_matrix()
+    timer = L.perftimer_malloc()
+    st = L.solver_init(L.lookup_solver_by_shortname(b"b200"), 0, 0, timer)
+    for _ in range(rep):
+        L.solver_solve(st, A, bm, x)
+    assert L.validate_matrix(x) == 0
+    out = mc.matrix_to_numpy(x)
+    ticks = {k: L.perftimer_tic_ms(timer, k.encode()) for k in ("analyze", "factorize", "evaluate")}
+    L.solver_finalize(st)
+    L.free_matrix(A); L.free_matrix(bm); L.free_matrix(x); L.perftimer_free(timer)
+    return out, ticks
+
+
+@pytest.mark.parametrize("mat,rhs,tol", GOLDEN_CASES)
+def test_known_answer_fixtures_through_plugin(mc, golden, mat, rhs, tol):
+    x, ticks = plugin_solve(mc, f"{golden}/{mat}.mm", b_path=None if rhs == "default" else f"{golden}/rhs1.mm")
+    e = read_mm_dense(f"{golden}/{mat}-{rhs}-ans.mm")
+    assert x.shape == e.shape and np.all(np.abs(x - e) <= tol), np.abs(x - e).max()
+    assert all(v >= 0 for v in ticks.values())       # the dispatcher's ticks were recorded
+
+
+@pytest.mark.parametrize("mat,rhs,tol", GOLDEN_CASES)
+def test_known_answer_fixtures_through_cli(mc, golden, mat, rhs, tol):
+    """testsuite.at:312-346 verbatim: --expected=... [--right-hand-side=rhs1.mm] --solver=b200 => PASS"""
+    args = [mc.CLI_PATH, f"--input={golden}/{mat}.mm", f"--expected={golden}/{mat}-{rhs}-ans.mm", "--solver=b200", f"--precision={tol}"]
+    if rhs == "rhs1":
+        args.append(f"--right-hand-side={golden}/rhs1.mm")
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert (r.returncode, r.stdout) == (0, "PASS\n"), (r.stdout, r.stderr)
+
+
+def test_cli_output_formats(mc, golden, tmp_path):
+    """testsuite.at:187-233: silent run, `-o -` print format, -b, -p 0 => FAIL(100), wrong answer => FAIL, -t CSV, -v"""
+    u = f"{golden}/unsym.mm"
+    r = subprocess.run([mc.CLI_PATH, "-i", u], capture_output=True, text=True); assert (r.returncode, r.stdout) == (0, "")
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-o", "-"], capture_output=True, text=True)
+    assert r.stdout == "  x(0)=1.00\n  x(1)=0.43\n  x(2)=0.25\n  x(3)=-0.09\n  x(4)=0.25\n"
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-b", f"{golden}/rhs1.mm", "-o", "-"], capture_output=True, text=True)
+    assert r.stdout == "  x(0)=1.00\n  x(1)=-0.04\n  x(2)=0.25\n  x(3)=-0.36\n  x(4)=0.25\n"
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-e", f"{golden}/unsym-default-ans.mm", "-p", "0"], capture_output=True, text=True)
+    assert (r.returncode, r.stdout) == (100, "FAIL\n")
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-e", f"{golden}/unsym-rhs1-ans.mm"], capture_output=True, text=True)
+    assert (r.returncode, r.stdout) == (100, "FAIL\n")
+    out = tmp_path / "x.mm"
+    r = subprocess.run([mc.CLI_PATH, "-i", f"{golden}/sym_posdef.mm", "-o", str(out)], capture_output=True, text=True); assert r.returncode == 0
+    got = read_mm_dense(str(out)); ref = read_mm_dense(f"{golden}/sym_posdef-default-ans.mm")
+    assert open(out).readline() == "%%MatrixMarket matrix coordinate real general\n" and np.all(np.abs(got - ref) <= 5e-12)
+    r = subprocess.run([mc.CLI_PATH, "-i", str(out), "-o", str(out)], capture_output=True, text=True); assert r.returncode == 1   # refuses to overwrite
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-t"], capture_output=True, text=True)
+    head, body = r.stdout.splitlines()
+    assert head == "status, solver, threads, rows, max. memory (MB),  total memory (MB), analyze, factorize, evaluate, total (ms)"
+    assert body.startswith("PASS, B200-multifrontal, 0, 5, ") and len(body.split(", ")) == 10
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-t", "-e", f"{golden}/unsym-default-ans.mm"], capture_output=True, text=True)
+    assert r.stdout.splitlines()[1].endswith("analyze, factorize, evaluate, done, total (ms)")     # the extra "test" tic (src/meagre-crowd.c:370)
+    assert subprocess.run([mc.CLI_PATH, "-i", u, "-t", "-r", "3"], capture_output=True, text=True).returncode == 0
+    r = subprocess.run([mc.CLI_PATH, "-i", u, "-v"], capture_output=True, text=True)
+    assert r.stdout.startswith("Ax=b: A is 5x5, nz=11, unsymmetric, real double, b is 5x1, nz=5\nsolved with B200-multifrontal on 0 cores, 0 threads\n")
+    for flags in ("-vv", "-vvv", "-tt", "-ttt", "-tttt"):
+        assert subprocess.run([mc.CLI_PATH, "-i", u, flags], capture_output=True, text=True).returncode == 0
+
+
+def test_repeated_solve_and_multiple_rhs_through_plugin(mc, golden):
+    """-r N calls analyze/factorize/evaluate N times on one state; a p-column b arrives in one call"""
+    A = read_mm_dense(f"{golden}/sym_posdef.mm")
+    B = np.stack([np.arange(5.0), np.array([4.0, 1, 2, 3, 4]), np.ones(5)], axis=1)
+    x, _ = plugin_solve(mc, f"{golden}/sym_posdef.mm", b=B, rep=3)
+    assert x.shape == (5, 3) and np.allclose(A @ x, B, atol=1e-11)
+
+
+CHOL_GRIDS = [("p2d-1x1", lambda: stencils.poisson2d_upper(1, 1)), ("p2d-3x2", lambda: stencils.poisson2d_upper(3, 2)),
+              ("p2d-33", lambda: stencils.poisson2d_upper(33)), ("p2d-130x7", lambda: stencils.poisson2d_upper(130, 7)),
+              ("p3d-11", lambda: stencils.poisson3d_upper(11)), ("p3d-20x13x9", lambda: stencils.poisson3d_upper(20, 13, 9)),
+              ("p3d-26", lambda: stencils.poisson3d_upper(26))]
+
+
+@pytest.mark.parametrize("name,gen", CHOL_GRIDS)
+@pytest.mark.parametrize("relax", [True, False])
+def test_cholesky_factor_and_solution_vs_oracle(mc, name, gen, relax):
+    n, cp, ri, v = gen()
+    v = v * (1.0 + 0.3 * np.abs(np.sin(np.arange(len(v)))) * (ri.astype(np.int64) == np.repeat(np.arange(n), np.diff(cp.astype(np.int64)))))   # non-constant diagonal, still diagonally dominant
+    s = mc.Solver()
+    s.analyze(n, cp, ri, 0, relax=relax)
+    assert s.factor(v) == 0, s.err()
+    d = sym_dict(mc, s.S)
+    pcp, pri, pvx = oracle.permuted_upper(n, cp, ri, v, d["perm"])
+    fac = oracle.chol_uplooking(n, pcp, pri, pvx)
+    # (1) the factor itself, column by column, against the oracle's L
+    flat = s.read_factor(0)
+    worst = 0.0
+    for sn in range(d["ns"]):
+        c0, c1 = d["sn_start"][sn], d["sn_start"][sn + 1]
+        rows = d["rowidx"][d["rowptr"][sn]:d["rowptr"][sn + 1]]; f = len(rows)
+        panel = flat[d["lptr"][sn]:d["lptr"][sn] + f * (c1 - c0)].reshape((f, c1 - c0), order="F")
+        for j in range(c0, c1):
+            col = np.zeros(n); col[rows[j - c0:]] = panel[j - c0:, j - c0]
+            ref = np.zeros(n); ref[fac["Li"][fac["Lp"][j]:fac["Lp"][j + 1]]] = fac["Lx"][fac["Lp"][j]:fac["Lp"][j + 1]]
+            worst = max(worst, np.abs(col - ref).max() / np.abs(ref).max())
+    assert worst <= 1e-12, worst
+    # (2) solutions for 1 and 5 right-hand sides against the oracle's solve
+    B = np.stack([np.arange(n, dtype=float), np.ones(n), np.cos(np.arange(n)), (np.arange(n) % 7) - 3.0, np.zeros(n)], axis=1)
+    X = s.solve(B); x1 = s.solve(B[:, 0])
+    assert np.array_equal(X[:, 0], x1)                      # same bits whatever the batch
+    A = stencils.to_scipy(n, cp, ri, v, True)
+    for k in range(B.shape[1]):
+        y = oracle.chol_solve(fac, B[d["perm"], k]); xo = np.empty(n); xo[d["perm"]] = y
+        scale = max(np.abs(xo).max(), 1e-300)
+        assert np.abs(X[:, k] - xo).max() <= 1e-11 * scale
+        if np.any(B[:, k]):
+            assert backward_error(A, X[:, k], B[:, k]) <= 1e-12
+    assert np.all(X[:, 4] == 0.0)
+    s.close()
+
+
+def test_factor_is_deterministic_and_refactorable(mc):
+    """idempotence: factoring the same values twice gives identical bits; new values reuse the analysis"""
+    n, cp, ri, v = stencils.poisson3d_upper(14)
+    s = mc.Solver(); s.analyze(n, cp, ri, 0)
+    assert s.factor(v) == 0; a = s.read_factor(0).copy()
+    assert s.factor(v) == 0; b = s.read_factor(0)
+    assert np.array_equal(a, b)
+    assert s.factor(2.0 * v) == 0
+    x = s.solve(np.ones(n)); A = stencils.to_scipy(n, cp, ri, 2.0 * v, True)
+    assert backward_error(A, x, np.ones(n)) <= 1e-12
+    s.close()
+
+
+def test_solve_is_linear(mc):
+    n, cp, ri, v = stencils.poisson2d_upper(50)
+    s = mc.Solver(); s.analyze(n, cp, ri, 0); assert s.factor(v) == 0
+    rng = np.random.default_rng(1); b1 = rng.standard_normal(n); b2 = rng.standard_normal(n)
+    x1, x2, x3 = s.solve(b1), s.solve(b2), s.solve(2.0 * b1 - 3.0 * b2)
+    assert np.abs(x3 - (2.0 * x1 - 3.0 * x2)).max() <= 1e-10 * np.abs(x3).max()
+    s.close()
+
+
+def test_not_positive_definite_is_reported_not_hidden(mc, golden):
+    Ad = read_mm_dense(f"{golden}/sym.mm")
+    U = sp.triu(sp.csc_matrix(Ad)).tocsc(); U.sort_indices()
+    s = mc.Solver(); s.analyze(5, U.indptr, U.indices, 0)
+    assert s.factor(U.data) == mc.B200_ERR_NOT_SPD and "positive definite" in s.err()
+    with pytest.raises(RuntimeError):
+        s.solve(np.ones(5))                       # no solve after a failed factor
+    s.close()
+
+
+LU_CASES = [("cd27-6", lambda: stencils.convdiff27_full(6)), ("cd27-12x9x7", lambda: stencils.convdiff27_full(12, 9, 7)),
+            ("cd27-16", lambda: stencils.convdiff27_full(16)), ("p3d-full-10", lambda: stencils.upper_to_full(*stencils.poisson3d_upper(10)))]
+
+
+@pytest.mark.parametrize("name,gen", LU_CASES)
+def test_lu_vs_oracle_and_backward_error(mc, name, gen):
+    n, cp, ri, v = gen()
+    s = mc.Solver(); s.analyze(n, cp, ri, 1)
+    assert s.factor(v) == 0, s.err()
+    assert s.stats().npiv_perturbed == 0
+    A = stencils.to_scipy(n, cp, ri, v)
+    B = np.stack([np.arange(n, dtype=float), np.sin(np.arange(n))], axis=1)
+    X = s.solve(B)
+    for k in range(2):
+        assert backward_error(A, X[:, k], B[:, k]) <= 1e-12
+    if n <= 1200:
+        Xo = oracle.dense_solve(A.toarray(), B)     # dense LU with partial pivoting (the UMFPACK/MUMPS class of answer)
+        assert np.abs(X - Xo).max() <= 1e-10 * np.abs(Xo).max()
+    import scipy.sparse.linalg as sla
+    Xs = sla.splu(A.tocsc()).solve(B)               # independent third party (SuperLU)
+    assert np.abs(X - Xs).max() <= 1e-9 * np.abs(Xs).max()
+    s.close()
+
+
+def test_lu_needs_pivoting_inside_the_front(mc, golden):
+    """tests/unsym.mm has zero diagonal entries: only row interchanges make it factorable"""
+    Ad = read_mm_dense(f"{golden}/unsym.mm")
+    assert Ad[1, 1] == 0 and Ad[2, 2] == 0
+    A = sp.csc_matrix(Ad); A.sort_indices()
+    s = mc.Solver(); s.analyze(5, A.indptr, A.indices, 1)
+    assert s.factor(A.data) == 0 and s.stats().npiv_perturbed == 0
+    x = s.solve(np.arange(5.0))
+    assert np.all(np.abs(x - read_mm_dense(f"{golden}/unsym-default-ans.mm")[:, 0]) <= 5e-14)
+    s.close()
+
+
+def test_headline_shape_properties_at_64cubed(mc):
+    """size-independent properties at a size the scalar oracle cannot reach in seconds:
+    backward error <= 1e-12, residual orthogonality free; agreement with the BLAS-3 CPU multifrontal oracle"""
+    n, cp, ri, v = stencils.poisson3d_upper(64)
+    s = mc.Solver(); S = s.analyze(n, cp, ri, 0)
+    assert s.factor(v) == 0, s.err()
+    b = np.arange(n, dtype=float)
+    x = s.solve(b)
+    A = stencils.to_scipy(n, cp, ri, v, True)
+    assert backward_error(A, x, b) <= 1e-12
+    d = sym_dict(mc, s.S)
+    oracle.load_blas()
+    panels = oracle.mf_cholesky(n, cp, ri, v, d)
+    xo = oracle.mf_solve(d, panels, b)
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+    # checksum of the factor: sum of squares of row i of L equals a_ii => trace identity
+    flat = s.read_factor(0)
+    tr = 0.0
+    for sn in range(d["ns"]):
+        k = d["sn_start"][sn + 1] - d["sn_start"][sn]; f = d["rowptr"][sn + 1] - d["rowptr"][sn]
+        p = flat[d["lptr"][sn]:d["lptr"][sn] + f * k].reshape((f, k), order="F")
+        tr += float((np.tril(p[:k]) ** 2).sum() + (p[k:] ** 2).sum())
+    assert abs(tr - 6.0 * n) <= 1e-9 * 6.0 * n          # ||L||_F^2 = trace(A)
+    s.close()
