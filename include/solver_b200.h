@@ -149,7 +149,8 @@ typedef struct b200_stats {
   double factor_ms;        /* whole factor on the device (events)            */
   double solve_ms;         /* whole solve on the device (events)             */
   double gemm_ms;          /* time in the DMMA trailing-update kernel        */
-  double gemm_flops;       /* flops executed by that kernel                  */
+  double gemm_flops;       /* flops executed by that kernel (whole tiles)    */
+  double gemm_alg_flops;   /* its share of the exact factor flops (no tile padding, no relaxation zeros) */
   int64_t launches;        /* kernels launched by the last factor            */
   int64_t solve_launches;  /* kernels launched by the last solve             */
   int64_t gemm_launches;
@@ -167,6 +168,7 @@ int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int6
 
 /* micro-benchmarks used to establish the FP64 roof on the box */
 double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ); /* our DMMA kernel */
+double b200_bench_fp64_peak_tflops( b200_ctx_t* c, int which, int iters );  /* 0: DMMA.8x8x4 issue roof, 1: DFMA roof */
 double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters );
 
 #ifdef __cplusplus

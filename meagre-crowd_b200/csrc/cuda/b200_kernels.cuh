@@ -643,6 +643,37 @@ __global__ void axpy_kernel( double* __restrict__ x, const double* __restrict__ 
   for ( ; e < tot; e += stride ) x[e] += d[e];
 }
 
+/* micro-benchmark: issue-rate roof of DMMA.8x8x4 (registers only, 16 independent accumulators per warp) */
+__global__ void __launch_bounds__( 256 ) dmma_peak_kernel( double* out, int iters ) {
+  double acc[16][2];
+#pragma unroll
+  for ( int i = 0; i < 16; i++ ) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for ( int it = 0; it < iters; it++ ) {
+#pragma unroll
+    for ( int i = 0; i < 16; i++ ) dmma884( acc[i][0], acc[i][1], a, b );
+  }
+  double s = 0.0;
+#pragma unroll
+  for ( int i = 0; i < 16; i++ ) s += acc[i][0] + acc[i][1];
+  if ( s == 12345.678 ) out[0] = s;
+}
+/* micro-benchmark: FP64 FMA pipe roof (DFMA, 16 independent chains per thread) */
+__global__ void __launch_bounds__( 256 ) dfma_peak_kernel( double* out, int iters ) {
+  double acc[16];
+#pragma unroll
+  for ( int i = 0; i < 16; i++ ) acc[i] = i;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for ( int it = 0; it < iters; it++ ) {
+#pragma unroll
+    for ( int i = 0; i < 16; i++ ) acc[i] = fma( acc[i], a, b );
+  }
+  double s = 0.0;
+#pragma unroll
+  for ( int i = 0; i < 16; i++ ) s += acc[i];
+  if ( s == 12345.678 ) out[0] = s;
+}
+
 /* micro-benchmark: plain streaming copy */
 __global__ void stream_copy_kernel( const double2* __restrict__ a, double2* __restrict__ b, int64_t n2 ) {
   int64_t i = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;

@@ -44,6 +44,7 @@ enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GE
 static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma_128", "gemm_dmma_64" };
 
 struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; };
+static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
 enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_DIAG, SK_FWD_UPDATE, SK_BWD_PARTIAL, SK_BWD_DIAG, SK_COUNT };
@@ -73,7 +74,7 @@ struct b200_ctx {
   std::vector<int64_t> level_cb;          /* doubles of CB used by each level */
   std::vector<int64_t> level_w;           /* solve workspace rows per level */
   int64_t w_rows[2] = { 0, 0 };
-  double flops_exact = 0, flops_stored = 0;
+  double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
   int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr;
@@ -154,6 +155,8 @@ static void add_gemm( std::vector<GemmTask>& tasks, std::vector<Tile>& big, std:
   GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = ldc; t.lda = lda; t.ldb = ldb; t.M = M; t.N = N; t.K = K; t.lower = lower; t.diag = diag;
   const int id = ( int )tasks.size();
   tasks.push_back( t );
+  if ( lower ) { const double nn = std::min( N, M + diag ); g_alg_flops += ( double )K * ( nn * ( nn + 1 ) + 2.0 * ( ( double )M + diag - nn ) * nn ); }
+  else g_alg_flops += 2.0 * M * N * K;
   const bool isbig = ( M > 96 && N > 96 ) || ( ( int64_t )M * N > 64 * 64 * 6 && M > 64 && N > 32 );
   const int bm = isbig ? 128 : 64, bn = isbig ? 128 : 64;
   std::vector<Tile>& tl = isbig ? big : small;
@@ -227,6 +230,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( c->sn.upload( meta ) ) return B200_ERR_CUDA;
 
   /* ---- factor schedule */
+  g_alg_flops = 0;
   std::vector<GemmTask> gt; std::vector<Tile> tb, ts; std::vector<DiagTask> dt; std::vector<TrsmTask> tt; std::vector<RowTile> ttl; std::vector<AsmTask> at;
   std::vector<Launch>& LS = c->launches;
   double* Lb = c->dL; double* Ub = c->dU;
@@ -335,6 +339,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
 
+  c->gemm_alg_flops = g_alg_flops;
   /* ---- solve schedule: forward deepest->root, backward root->deepest */
   std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<int> gp;
   std::vector<SLaunch>& SS = c->slaunches;
@@ -437,6 +442,7 @@ static int run_factor( b200_ctx* c ) {
   CK( cudaStreamSynchronize( st ) );
   float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
   c->stats.factor_ms = ms; c->stats.launches = nlaunch; c->stats.gemm_flops = gemm_flops; c->stats.gemm_launches = gemm_launches;
+  c->stats.gemm_alg_flops = c->gemm_alg_flops * ( c->flops_stored > 0 ? c->flops_exact / c->flops_stored : 1.0 );
   c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] + c->prof_ms[LK_GEMM_SMALL] : 0.0;
   c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes;
   if ( err != 0 ) { char a[64]; snprintf( a, 64, "%d", err - 1 ); set_err( "matrix is not positive definite (pivot column %s of the permuted matrix)%s", a, "" ); c->factored = false; return B200_ERR_NOT_SPD; }
@@ -633,6 +639,24 @@ extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, i
   dgt.release(); dtb.release(); dts.release(); cudaFree( A ); cudaFree( B ); cudaFree( C );
   if ( cudaGetLastError() != cudaSuccess ) return -1.0;
   return 2.0 * m * n * ( double )k / ( best * 1e-3 ) / 1e12;
+}
+
+/* which: 0 = DMMA.8x8x4 issue roof, 1 = DFMA roof; TFLOP/s, best of iters */
+extern "C" double b200_bench_fp64_peak_tflops( b200_ctx_t* c, int which, int iters ) {
+  if ( !c ) return -1.0;
+  cudaSetDevice( c->device );
+  double* out; if ( cudaMalloc( &out, 8 ) ) return -1.0;
+  const int inner = 4096, blocks = 148 * 8;
+  float best = 1e30f;
+  for ( int it = 0; it < iters + 2; it++ ) {
+    cudaEventRecord( c->ev0, c->stream );
+    if ( which == 0 ) dmma_peak_kernel<<<blocks, 256, 0, c->stream>>>( out, inner ); else dfma_peak_kernel<<<blocks, 256, 0, c->stream>>>( out, inner );
+    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
+    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
+  }
+  cudaFree( out );
+  const double flops = which == 0 ? ( double )blocks * 8 * inner * 16 * 512.0 : ( double )blocks * 256 * inner * 16 * 2.0;
+  return flops / ( best * 1e-3 ) / 1e12;
 }
 
 extern "C" double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters ) {
