@@ -170,6 +170,7 @@ def main():
     b = np.arange(n, dtype=np.float64)
     d_b = L.b200_dev_alloc(ctx, b.nbytes); d_x = L.b200_dev_alloc(ctx, b.nbytes); L.b200_dev_upload(ctx, d_b, b.ctypes.data, b.nbytes)
     st = m.b200_stats_t()
+    refine = [0]
 
     def step():
         r = L.b200_factor_device(ctx, d_vals)
@@ -180,6 +181,7 @@ def main():
         if r != 0:
             raise RuntimeError("solve failed: " + s.err())
         L.b200_get_stats(ctx, C.byref(st))
+        refine[0] = st.refine_steps
         return fms, st.solve_ms, nl + st.solve_launches
 
     def barrier():
@@ -227,7 +229,7 @@ def main():
         dmma_peak = L.b200_bench_fp64_peak_tflops(ctx, 0, 3); dfma_peak = L.b200_bench_fp64_peak_tflops(ctx, 1, 3)
         peak = 37.0   # nominal HGX B200 FP64 (tensor = vector); MEASURED_PEAKS.json has no FP64 entry -- see DESIGN.md
         achieved = gemm_alg / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        roofline = {"bound": "tensor", "kernel": "gemm_nt_dmma_kernel (DMMA.8x8x4, 128x128 and 64x64 tiles)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roofline = {"bound": "tensor", "kernel": "gemm_nt_dmma_kernel (DMMA.8x8x4, 64x64 CTA tile, 3 CTAs/SM)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if achieved else None, "traffic": None,
                     "peak_source": "nominal FP64 37 TFLOP/s (HGX B200 datasheet; not in MEASURED_PEAKS.json)",
                     "measured_dmma_issue_roof_tflops": dmma_peak, "measured_dfma_roof_tflops": dfma_peak,
@@ -236,7 +238,7 @@ def main():
                     "kernel_ms": {k: v_[1] for k, v_ in prof.items()}}
         extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "backward_error": berr,
                  "n": n, "nnz_L": int(S.nnzL), "stored_nnz_L": int(S.stored_nnzL), "factor_flops": F, "supernodes": S.ns, "levels": S.maxdepth + 1, "max_front": S.maxfront,
-                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * 2 / solve_s / 1e9}
+                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0]}
     # release the device-resident copy before the plugin path allocates its own
     L.b200_dev_free(ctx, d_vals); L.b200_dev_free(ctx, d_b); L.b200_dev_free(ctx, d_x)
     s.close()
@@ -268,7 +270,7 @@ def main():
     if rank == 0:
         line = {"metric": "fp64_factor_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"poisson3d_7pt_{args.grid}^3_spd_cholesky", "step": "factorize + evaluate(p=1, 1 refinement step), values and b resident in HBM",
+                "config": {"workload": f"poisson3d_7pt_{args.grid}^3_spd_cholesky", "step": "factorize + evaluate(p=1, automatic refinement), values and b resident in HBM",
                            "ordering": "nested dissection (own)", "l2": "inputs larger than L2 (factor touches >18 GB per step)",
                            "multi_gpu": "replicas (one full problem per rank)" if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}

@@ -140,8 +140,10 @@ void b200_host_free_pinned( void* p );
 int b200_dev_sync( b200_ctx_t* c );
 int b200_flush_l2( b200_ctx_t* c );             /* write a >L2 buffer between timed steps */
 
-/* iterative refinement steps per solve (default 1): r = b - A x is accumulated in
- * double-double on the device, then one more pair of sweeps corrects x */
+/* iterative refinement: r = b - A x is accumulated in double-double on the device, then one more
+ * pair of sweeps corrects x.  steps >= 0: exactly that many; steps < 0 (default): automatic -- one
+ * step for small systems (n*p <= 65536), otherwise only while the componentwise backward error
+ * max_i |r_i| / (|A||x|+|b|)_i is above 1e-15 (at most 2 steps) */
 int b200_set_refinement( b200_ctx_t* c, int steps );
 
 /* statistics of the last factor / solve (device-event milliseconds) */
@@ -157,6 +159,8 @@ typedef struct b200_stats {
   double h2d_ms, d2h_ms;
   int64_t device_bytes;    /* bytes of HBM held by the context               */
   int npiv_perturbed;      /* LU: statically perturbed pivots                */
+  int refine_steps;        /* refinement steps taken by the last solve       */
+  double backward_error;   /* componentwise backward error seen before the last decision (automatic mode), else -1 */
 } b200_stats_t;
 int b200_get_stats( b200_ctx_t* c, b200_stats_t* out );
 /* per-kernel timing of the next factor (serialises launches; diagnostics only) */
@@ -168,6 +172,8 @@ int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int6
 
 /* micro-benchmarks used to establish the FP64 roof on the box */
 double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ); /* our DMMA kernel */
+double b200_bench_dgemm_variant( b200_ctx_t* c, int variant, int m, int n, int k, int iters );   /* tile-shape tuning aid */
+double b200_bench_dmma_occupancy( b200_ctx_t* c, int warps_per_sm, int ilp );   /* DMMA rate vs resident warps / independent accumulators */
 double b200_bench_fp64_peak_tflops( b200_ctx_t* c, int which, int iters );  /* 0: DMMA.8x8x4 issue roof, 1: DFMA roof */
 double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters );
 

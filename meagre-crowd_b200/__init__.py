@@ -60,7 +60,7 @@ class b200_symbolic_t(C.Structure):
 class b200_stats_t(C.Structure):
     _fields_ = [("factor_ms", C.c_double), ("solve_ms", C.c_double), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double), ("gemm_alg_flops", C.c_double),
                 ("launches", C.c_int64), ("solve_launches", C.c_int64), ("gemm_launches", C.c_int64),
-                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("device_bytes", C.c_int64), ("npiv_perturbed", C.c_int)]
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("device_bytes", C.c_int64), ("npiv_perturbed", C.c_int), ("refine_steps", C.c_int), ("backward_error", C.c_double)]
 
 
 # every symbol include/*.h declares (checked by tests/test_abi.py)
@@ -80,7 +80,7 @@ EXPORTED_SYMBOLS = [
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_upload_symbolic", "b200_factor_host", "b200_factor_device",
     "b200_solve_host", "b200_solve_device", "b200_dev_alloc", "b200_dev_free", "b200_dev_upload", "b200_dev_download",
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
-    "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
+    "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dgemm_variant", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
 ]
 
 _lib = None
@@ -152,6 +152,8 @@ def lib():
     L.b200_set_refinement.argtypes = [vp, i32]
     L.b200_debug_read.argtypes = [vp, i32, vp, i64, i64]
     L.b200_bench_dgemm_tflops.restype = dbl; L.b200_bench_dgemm_tflops.argtypes = [vp, i32, i32, i32, i32]
+    L.b200_bench_dgemm_variant.restype = dbl; L.b200_bench_dgemm_variant.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.b200_bench_dmma_occupancy.restype = dbl; L.b200_bench_dmma_occupancy.argtypes = [vp, i32, i32]
     L.b200_bench_fp64_peak_tflops.restype = dbl; L.b200_bench_fp64_peak_tflops.argtypes = [vp, i32, i32]
     L.b200_bench_stream_gbs.restype = dbl; L.b200_bench_stream_gbs.argtypes = [vp, C.c_size_t, i32]
     _lib = L

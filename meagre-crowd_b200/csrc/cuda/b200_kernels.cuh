@@ -332,9 +332,8 @@ __global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __res
  * stored k-major with a row stride of BM+4 doubles so that the m8n8k4 fragment
  * reads (lane>>2 -> m, lane&3 -> k) hit 32 distinct banks.  Each warp owns a
  * WM x WN sub-tile = (WM/8)x(WN/8) DMMA.8x8x4 accumulators in registers. */
-template <int BM, int BN, int WM, int WN, int STAGES>
+template <int BM, int BN, int WM, int WN, int STAGES, int BK = 16>
 __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles ) {
-  constexpr int BK = 16;
   constexpr int NT = ( BM / WM ) * ( BN / WN ) * 32;
   constexpr int LDA = BM + 4, LDB = BN + 4;
   constexpr int MT = WM / 8, NTL = WN / 8;
@@ -475,142 +474,181 @@ __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const int* __restric
   }
 }
 
-/* z = T * P * y_b  (T = inverse of the block's lower factor), written back in place */
-__global__ void __launch_bounds__( 64 ) fwd_diag_kernel( const SolveBlk* __restrict__ blks, const SnMeta* __restrict__ sn, const double* __restrict__ inv,
-                                                         const int* __restrict__ piv, double* __restrict__ y, int n, int p ) {
+/* Forward sweep, one launch per 64-column block step of a tree level.
+ * Every CTA of a block first forms z = T * P * y_b in shared memory (T = inverse of the block's
+ * triangular factor, 32 KB from L2; recomputing it per CTA removes a separate launch from the
+ * dependency chain), then updates its 256 rows below the block: y/w -= L[rows, block] * z.
+ * The CTA of the first tile also stores z (the finished forward values) into Z. */
+__global__ void __launch_bounds__( 256 ) fwd_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                           const double* __restrict__ L, const double* __restrict__ inv, const int* __restrict__ piv,
+                                                           double* __restrict__ y, double* __restrict__ Z, int n, int p, double* __restrict__ w, int64_t ldw ) {
   __shared__ double ys[NB][PC];
-  const SolveBlk b = blks[blockIdx.x];
-  const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int r = threadIdx.x, nb = b.nb;
-  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
-  double* yb = y + S.c0 + b.j0;
-  if ( r < nb ) for ( int q = 0; q < pcn; q++ ) ys[r][q] = yb[r + ( int64_t )( pc0 + q ) * n];
-  __syncthreads();
-  if ( piv ) {
-    if ( r < pcn ) { const int* pv = piv + S.c0 + b.j0; for ( int j = 0; j < nb; j++ ) { int pj = pv[j]; if ( pj != j ) { double t = ys[j][r]; ys[j][r] = ys[pj][r]; ys[pj][r] = t; } } }
-    __syncthreads();
-  }
-  if ( r < nb ) {
-    double acc[PC];
-#pragma unroll
-    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-    for ( int c = 0; c <= r; c++ ) {
-      const double tv = T[r + c * nb];
-#pragma unroll
-      for ( int q = 0; q < PC; q++ ) acc[q] += tv * ys[c][q];
-    }
-    for ( int q = 0; q < pcn; q++ ) yb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
-  }
-}
-
-/* rows below the block: y/w -= L[rows, block] * z ; one thread per row, 256 rows per CTA */
-__global__ void __launch_bounds__( 256 ) fwd_update_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                            const double* __restrict__ L, double* __restrict__ y, int n, int p,
-                                                            double* __restrict__ w, int64_t ldw ) {
   __shared__ double zs[NB][PC];
   const RowTile rt = tiles[blockIdx.x];
   const SolveBlk b = blks[rt.task];
   const SnMeta S = sn[b.sn];
   const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int nb = b.nb;
-  for ( int e = threadIdx.x; e < nb * PC; e += 256 ) { int r = e / PC, q = e % PC; zs[r][q] = q < pcn ? y[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] : 0.0; }
+  const int nb = b.nb, tid = threadIdx.x;
+  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
+  for ( int e = tid; e < NB * PC; e += 256 ) { const int r = e / PC, q = e % PC; ys[r][q] = ( r < nb && q < pcn ) ? y[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] : 0.0; }
   __syncthreads();
-  const int lr = b.j0 + nb + rt.r0 + threadIdx.x;   /* front-local row */
+  if ( piv ) {
+    if ( tid < pcn ) { const int* pv = piv + S.c0 + b.j0; for ( int j = 0; j < nb; j++ ) { const int pj = pv[j]; if ( pj != j ) { const double t = ys[j][tid]; ys[j][tid] = ys[pj][tid]; ys[pj][tid] = t; } } }
+    __syncthreads();
+  }
+  {
+    const int r = tid >> 2, part = tid & 3;
+    double acc[PC];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+    {
+      double tv[NB / 4];
+#pragma unroll
+      for ( int i = 0; i < NB / 4; i++ ) { const int c = part + 4 * i; tv[i] = ( r < nb && c <= r ) ? __ldg( T + r + c * nb ) : 0.0; }   /* 16 independent loads in flight */
+#pragma unroll
+      for ( int i = 0; i < NB / 4; i++ ) {
+        const int c = part + 4 * i;
+#pragma unroll
+        for ( int q = 0; q < PC; q++ ) acc[q] += tv[i] * ys[c][q];
+      }
+    }
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) { acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 1 ); acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 2 ); }
+    if ( part == 0 ) {
+#pragma unroll
+      for ( int q = 0; q < PC; q++ ) zs[r][q] = acc[q];
+    }
+  }
+  __syncthreads();
+  if ( rt.r0 == 0 ) for ( int e = tid; e < nb * pcn; e += 256 ) { const int r = e % nb, q = e / nb; Z[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] = zs[r][q]; }
+  const int lr = b.j0 + nb + rt.r0 + tid;   /* front-local row */
   if ( lr >= S.f ) return;
   const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.f;
   double acc[PC];
 #pragma unroll
   for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-  for ( int c = 0; c < nb; c++ ) {
-    const double lv = Lr[( int64_t )c * S.f];
+  for ( int c0 = 0; c0 < nb; c0 += 16 ) {
+    double lv[16];
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) acc[q] += lv * zs[c][q];
+    for ( int i = 0; i < 16; i++ ) lv[i] = ( c0 + i < nb ) ? Lr[( int64_t )( c0 + i ) * S.f] : 0.0;      /* 16 independent loads in flight */
+#pragma unroll
+    for ( int i = 0; i < 16; i++ ) {
+#pragma unroll
+      for ( int q = 0; q < PC; q++ ) acc[q] += lv[i] * zs[( c0 + i ) & ( NB - 1 )][q];
+    }
   }
   if ( lr < S.k ) { for ( int q = 0; q < pcn; q++ ) y[S.c0 + lr + ( int64_t )( pc0 + q ) * n] -= acc[q]; }
   else { for ( int q = 0; q < pcn; q++ ) w[S.wptr + ( lr - S.k ) + ( int64_t )( pc0 + q ) * ldw] -= acc[q]; }
 }
 
-/* backward, stage 1: partial[tile][c][q] = sum over the tile's rows of M[row, block col c] * x[row]
- * M = L panel (Cholesky: L' x) or the U' panel / pivot-block rows (LU). 1024 rows per CTA;
- * each warp owns block columns c = warp, warp+8, ..; lanes stride over rows (coalesced). */
-constexpr int BWD_ROWS = 1024;
-template <bool LU>
-__global__ void __launch_bounds__( 256 ) bwd_partial_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                             const double* __restrict__ L, const double* __restrict__ U, const int* __restrict__ rowidx,
-                                                             const double* __restrict__ x, int n, int p, double* __restrict__ partial ) {
-  __shared__ double xs[PC / 2][BWD_ROWS];   /* two passes of PC/2 right-hand sides keep this at 32 KB */
+/* Backward sweep, one launch per block step.  Each CTA reduces its 256 rows below the block:
+ * partial[c] = sum_r M[row r, block col c] * x[row r]   (M = L panel: L' x; LU: the U' panel: U x),
+ * warps own block columns, lanes stride over rows (coalesced).  The last CTA of a block to finish
+ * (atomic ticket) sums the partials in tile order -- deterministic -- and forms
+ * x_b = T' (z_b - sum) in place in Z. */
+constexpr int BWD_ROWS = 256;
+__global__ void __launch_bounds__( 256 ) bwd_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                           const double* __restrict__ M, const double* __restrict__ inv, const int* __restrict__ rowidx,
+                                                           double* __restrict__ x, int n, int p, double* __restrict__ partial, unsigned int* __restrict__ tickets ) {
+  __shared__ double xs[PC][BWD_ROWS];
+  __shared__ double rs[NB][PC + 1];
+  __shared__ int is_last;
   const RowTile rt = tiles[blockIdx.x];
   const SolveBlk b = blks[rt.task];
   const SnMeta S = sn[b.sn];
   const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int nb = b.nb, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int base = b.j0 + nb + rt.r0;                     /* first front-local row of the tile */
-  const int rows = min( BWD_ROWS, S.f - base );
+  const int nb = b.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int base = b.j0 + nb + rt.r0;
+  const int rows = max( 0, min( BWD_ROWS, S.f - base ) );
   const int tile_in_blk = rt.r0 / BWD_ROWS;
   double* out = partial + ( ( int64_t )( b.first_partial + tile_in_blk ) * gridDim.y + blockIdx.y ) * NB * PC;
   const int* ri = rowidx + S.rowptr;
-  for ( int half = 0; half < 2; half++ ) {
-    const int h0 = half * ( PC / 2 );
-    __syncthreads();
-    for ( int e = threadIdx.x; e < rows * ( PC / 2 ); e += 256 ) {
-      const int r = e % rows, q = e / rows;
-      const int lr = base + r;
-      const int g = lr < S.k ? S.c0 + lr : ri[lr];
-      xs[q][r] = ( h0 + q < pcn ) ? x[g + ( int64_t )( pc0 + h0 + q ) * n] : 0.0;
-    }
-    __syncthreads();
-    for ( int c = warp; c < nb; c += 8 ) {
-      double acc[PC / 2];
-#pragma unroll
-      for ( int q = 0; q < PC / 2; q++ ) acc[q] = 0.0;
-      {
-        /* Cholesky: column of the L panel (L' x).  LU: the same column of the U' panel (U x). */
-        const double* col = ( LU ? U : L ) + S.lptr + base + ( int64_t )( b.j0 + c ) * S.f;
-        for ( int r = lane; r < rows; r += 32 ) {
-          const double lv = col[r];
-#pragma unroll
-          for ( int q = 0; q < PC / 2; q++ ) acc[q] += lv * xs[q][r];
-        }
-      }
-#pragma unroll
-      for ( int q = 0; q < PC / 2; q++ ) {
-        double v = acc[q];
-        for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
-        if ( lane == 0 ) out[c * PC + h0 + q] = v;
-      }
-    }
-  }
-}
-
-/* backward, stage 2: x_b = T' (y_b - sum of partials)   (Cholesky: T = inv(L); LU: T' = inv(U), stored transposed) */
-__global__ void __launch_bounds__( 64 ) bwd_diag_kernel( const SolveBlk* __restrict__ blks, const SnMeta* __restrict__ sn, const double* __restrict__ inv,
-                                                         double* __restrict__ x, int n, int p, const double* __restrict__ partial ) {
-  __shared__ double rs[NB][PC];
-  const SolveBlk b = blks[blockIdx.x];
-  const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int r = threadIdx.x, nb = b.nb;
-  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
-  double* xb = x + S.c0 + b.j0;
-  if ( r < nb ) {
-    for ( int q = 0; q < PC; q++ ) {
-      double v = q < pcn ? xb[r + ( int64_t )( pc0 + q ) * n] : 0.0;
-      for ( int t = 0; t < b.ntiles; t++ ) v -= partial[( ( int64_t )( b.first_partial + t ) * gridDim.y + blockIdx.y ) * NB * PC + r * PC + q];
-      rs[r][q] = v;
-    }
+  for ( int e = tid; e < rows * pcn; e += 256 ) {
+    const int r = e % rows, q = e / rows;
+    const int lr = base + r;
+    const int g = lr < S.k ? S.c0 + lr : ri[lr];
+    xs[q][r] = x[g + ( int64_t )( pc0 + q ) * n];
   }
   __syncthreads();
-  if ( r < nb ) {
+  for ( int c = warp; c < nb; c += 8 ) {
+    const double* col = M + S.lptr + base + ( int64_t )( b.j0 + c ) * S.f;
+    double lv[BWD_ROWS / 32];
+#pragma unroll
+    for ( int i = 0; i < BWD_ROWS / 32; i++ ) { const int r = lane + 32 * i; lv[i] = r < rows ? col[r] : 0.0; }   /* 8 independent coalesced loads */
     double acc[PC];
 #pragma unroll
     for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-    for ( int c = r; c < nb; c++ ) {       /* x[r] = sum_{c>=r} T[c,r] rs[c] */
-      const double tv = T[c + r * nb];
 #pragma unroll
-      for ( int q = 0; q < PC; q++ ) acc[q] += tv * rs[c][q];
+    for ( int i = 0; i < BWD_ROWS / 32; i++ ) {
+      const int r = lane + 32 * i;
+#pragma unroll
+      for ( int q = 0; q < PC; q++ ) if ( q < pcn ) acc[q] += lv[i] * ( r < rows ? xs[q][r] : 0.0 );
     }
-    for ( int q = 0; q < pcn; q++ ) xb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) if ( q < pcn ) {
+        double v = acc[q];
+        for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+        if ( lane == 0 ) out[c * PC + q] = v;
+      }
+  }
+  __threadfence();
+  __syncthreads();
+  if ( tid == 0 ) {
+    unsigned int* tk = tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y;
+    const unsigned int old = atomicAdd( tk, 1u );
+    is_last = ( old == ( unsigned int )( b.ntiles - 1 ) );
+    if ( is_last ) *tk = 0u;     /* ready for the next solve */
+  }
+  __syncthreads();
+  if ( !is_last ) return;
+  __threadfence();
+  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
+  double* xb = x + S.c0 + b.j0;
+  {
+    /* sum the tiles' partials: four thread groups take tiles t = g, g+4, ...; combined in a fixed order */
+    double* ps = &xs[0][0];                         /* reuse: [4][NB*PC] */
+    const int g = tid >> 6, e0 = tid & 63;
+    for ( int e = e0; e < nb * pcn; e += 64 ) {
+      const int r = e % nb, q = e / nb;
+      const double* pp = partial + ( ( int64_t )b.first_partial * gridDim.y + blockIdx.y ) * NB * PC + r * PC + q;
+      double v = 0.0;
+      int t = g;
+      for ( ; t + 12 < b.ntiles; t += 16 ) {
+        const double a0 = __ldcg( pp + ( int64_t )t * gridDim.y * NB * PC ), a1 = __ldcg( pp + ( int64_t )( t + 4 ) * gridDim.y * NB * PC ),
+                     a2 = __ldcg( pp + ( int64_t )( t + 8 ) * gridDim.y * NB * PC ), a3 = __ldcg( pp + ( int64_t )( t + 12 ) * gridDim.y * NB * PC );
+        v += a0; v += a1; v += a2; v += a3;
+      }
+      for ( ; t < b.ntiles; t += 4 ) v += __ldcg( pp + ( int64_t )t * gridDim.y * NB * PC );
+      ps[g * NB * PC + r * PC + q] = v;
+    }
+    __syncthreads();
+    for ( int e = tid; e < NB * pcn; e += 256 ) {
+      const int r = e % NB, q = e / NB;
+      if ( r >= nb ) { rs[r][q] = 0.0; continue; }
+      const double sum = ( ( ps[r * PC + q] + ps[NB * PC + r * PC + q] ) + ps[2 * NB * PC + r * PC + q] ) + ps[3 * NB * PC + r * PC + q];
+      rs[r][q] = xb[r + ( int64_t )( pc0 + q ) * n] - sum;
+    }
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 2, part = tid & 3;     /* x[r] = sum_{c>=r} T[c,r] rs[c] */
+    double acc[PC];
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+    {
+      double tv[NB / 4];
+#pragma unroll
+      for ( int i = 0; i < NB / 4; i++ ) { const int c = part + 4 * i; tv[i] = ( r < nb && c >= r && c < nb ) ? __ldg( T + c + r * nb ) : 0.0; }
+#pragma unroll
+      for ( int i = 0; i < NB / 4; i++ ) {
+        const int c = part + 4 * i;
+#pragma unroll
+        for ( int q = 0; q < PC; q++ ) if ( q < pcn ) acc[q] += tv[i] * rs[c][q];
+      }
+    }
+#pragma unroll
+    for ( int q = 0; q < PC; q++ ) { acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 1 ); acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 2 ); }
+    if ( part == 0 && r < nb ) for ( int q = 0; q < pcn; q++ ) xb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
   }
 }
 
@@ -618,13 +656,14 @@ __global__ void __launch_bounds__( 64 ) bwd_diag_kernel( const SolveBlk* __restr
  * fma, Knuth two-sum), so that one refinement step recovers x to working accuracy */
 __global__ void residual_dd_kernel( const int64_t* __restrict__ rp, const int* __restrict__ col, const int* __restrict__ src,
                                     const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ b,
-                                    int n, int p, double* __restrict__ r ) {
+                                    int n, int p, double* __restrict__ r, unsigned long long* __restrict__ omega_bits ) {
   int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
+  double omega = 0.0;   /* componentwise backward error max_i |r_i| / (|A||x| + |b|)_i  (Oettli-Prager) */
   for ( ; e < tot; e += stride ) {
     const int i = ( int )( e % n ); const int64_t c = e / n;
     const double* xc = x + c * n;
-    double hi = b[e], lo = 0.0;
+    double hi = b[e], lo = 0.0, den = fabs( b[e] );
     for ( int64_t q = rp[i]; q < rp[i + 1]; q++ ) {
       const double a = vals[src[q]], xv = xc[col[q]];
       const double pr = -a * xv;
@@ -633,9 +672,14 @@ __global__ void residual_dd_kernel( const int64_t* __restrict__ rp, const int* _
       const double bb = s - hi;
       const double se = ( hi - ( s - bb ) ) + ( pr - bb );
       hi = s; lo += se + pe;
+      den += fabs( pr );
     }
-    r[e] = hi + lo;
+    const double ri = hi + lo;
+    r[e] = ri;
+    if ( den > 0.0 ) omega = fmax( omega, fabs( ri ) / den );
   }
+  for ( int o = 16; o; o >>= 1 ) omega = fmax( omega, __shfl_xor_sync( 0xffffffffu, omega, o ) );
+  if ( ( threadIdx.x & 31 ) == 0 && omega > 0.0 ) atomicMax( omega_bits, ( unsigned long long )__double_as_longlong( omega ) );   /* positive doubles order like integers */
 }
 __global__ void axpy_kernel( double* __restrict__ x, const double* __restrict__ d, int64_t tot ) {
   int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
@@ -656,6 +700,21 @@ __global__ void __launch_bounds__( 256 ) dmma_peak_kernel( double* out, int iter
   double s = 0.0;
 #pragma unroll
   for ( int i = 0; i < 16; i++ ) s += acc[i][0] + acc[i][1];
+  if ( s == 12345.678 ) out[0] = s;
+}
+template <int ILP>
+__global__ void dmma_occ_kernel( double* out, int iters ) {
+  double acc[ILP][2];
+#pragma unroll
+  for ( int i = 0; i < ILP; i++ ) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for ( int it = 0; it < iters; it++ ) {
+#pragma unroll
+    for ( int i = 0; i < ILP; i++ ) dmma884( acc[i][0], acc[i][1], a, b );
+  }
+  double s = 0.0;
+#pragma unroll
+  for ( int i = 0; i < ILP; i++ ) s += acc[i][0] + acc[i][1];
   if ( s == 12345.678 ) out[0] = s;
 }
 /* micro-benchmark: FP64 FMA pipe roof (DFMA, 16 independent chains per thread) */

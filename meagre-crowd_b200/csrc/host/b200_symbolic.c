@@ -95,20 +95,21 @@ static void postorder( int n, const int* parent, const int* key, int* post ) {
   free( head ); free( next ); free( stack ); free( order );
 }
 
-/* Gilbert-Ng-Peyton column counts for a POSTORDERED matrix (post = identity).
- * lp/li: strictly-lower pattern by column (rows i>j in column j). */
-static void colcounts_postordered( int n, const int* parent, const int* lp, const int* li, int* cc ) {
+/* Gilbert-Ng-Peyton column counts.  post[k] = k-th node of a postorder of the etree
+ * (NULL: the matrix is already postordered).  lp/li: strictly-lower pattern by column. */
+static void colcounts_post( int n, const int* parent, const int* post, const int* lp, const int* li, int* cc ) {
   int* first = malloc( sizeof( int ) * n );
   int* maxfirst = malloc( sizeof( int ) * n );
   int* prevleaf = malloc( sizeof( int ) * n );
   int* anc = malloc( sizeof( int ) * n );
   for ( int j = 0; j < n; j++ ) { first[j] = -1; maxfirst[j] = -1; prevleaf[j] = -1; anc[j] = j; }
   for ( int k = 0; k < n; k++ ) {
-    int j = k;
+    int j = post ? post[k] : k;
     cc[j] = ( first[j] == -1 ) ? 1 : 0;   /* leaves of the etree start at 1 */
     for ( ; j != -1 && first[j] == -1; j = parent[j] ) first[j] = k;
   }
-  for ( int j = 0; j < n; j++ ) {
+  for ( int k = 0; k < n; k++ ) {
+    const int j = post ? post[k] : k;
     if ( parent[j] != -1 ) cc[parent[j]]--;            /* j is not a root */
     for ( int p = lp[j]; p < lp[j + 1]; p++ ) {
       int i = li[p];
@@ -126,9 +127,10 @@ static void colcounts_postordered( int n, const int* parent, const int* lp, cons
     }
     if ( parent[j] != -1 ) anc[j] = parent[j];
   }
-  for ( int j = 0; j < n; j++ ) if ( parent[j] != -1 ) cc[parent[j]] += cc[j];
+  for ( int k = 0; k < n; k++ ) { const int j = post ? post[k] : k; if ( parent[j] != -1 ) cc[parent[j]] += cc[j]; }
   free( first ); free( maxfirst ); free( prevleaf ); free( anc );
 }
+static void colcounts_postordered( int n, const int* parent, const int* lp, const int* li, int* cc ) { colcounts_post( n, parent, NULL, lp, li, cc ); }
 
 static int cmp_int( const void* a, const void* b ) { int x = *( const int* )a, y = *( const int* )b; return ( x > y ) - ( x < y ); }
 
@@ -282,36 +284,91 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
   S->nfund = nf;
   free( nchild );
 
-  /* ---- 4. relaxed amalgamation: merge a supernode into the next one when that is its parent */
-  int* merged = calloc( nf + 1, sizeof( int ) ); /* merged[s]=1: s is fused with s+1 */
-  if ( opts.relax ) {
-    double* gk = malloc( sizeof( double ) * nf ); /* columns of the group ending at s */
-    double* gf = malloc( sizeof( double ) * nf ); /* front order of the group          */
-    double* gz = malloc( sizeof( double ) * nf ); /* explicit zeros in the group        */
-    for ( int s = 0; s < nf; s++ ) { gk[s] = fstart[s + 1] - fstart[s]; gf[s] = cc[fstart[s]]; gz[s] = 0; }
-    for ( int s = 0; s + 1 < nf; s++ ) {
-      int last = fstart[s + 1] - 1;
-      if ( parent[last] != fstart[s + 1] ) continue; /* s+1 is not the parent of s */
-      double kc = gk[s], fc = gf[s], zc = gz[s];
-      double kp = gk[s + 1], fp = gf[s + 1], zp = gz[s + 1];
-      double k = kc + kp, f = kc + fp;
-      double tot = panel_nnz( k, f );
-      double z = tot - ( panel_nnz( kc, fc ) - zc ) - ( panel_nnz( kp, fp ) - zp );
-      double frac = z / tot;
-      int ok = 0;
-      if ( k <= opts.nrelax[0] ) ok = 1;
-      else if ( k <= opts.nrelax[1] ) ok = frac < opts.zrelax[0];
-      else if ( k <= opts.nrelax[2] ) ok = frac < opts.zrelax[1];
-      else ok = frac < opts.zrelax[2];
-      if ( ok ) { merged[s] = 1; gk[s + 1] = k; gf[s + 1] = f; gz[s + 1] = z; }
-    }
-    free( gk ); free( gf ); free( gz );
-  }
+  /* ---- 4. relaxed amalgamation on the supernodal tree (Ashcraft-Grimes): a child may be absorbed by
+   * its parent whichever position it has among the siblings; the columns are renumbered afterwards so
+   * that every merged group is contiguous (any topological order of the etree gives the same fill).
+   * A merge is accepted when (a) the merged front still fits one 64x64 device tile, or (b) the fraction
+   * of explicit zeros stays under CHOLMOD's documented tiers (nrelax {4,16,48}, zrelax {0.8,0.1,0.05}). */
   int ns = 0;
   int* sn_start = malloc( sizeof( int ) * ( nf + 1 ) );
-  for ( int s = 0; s < nf; s++ ) if ( s == 0 || !merged[s - 1] ) sn_start[ns++] = fstart[s];
-  sn_start[ns] = n;
-  free( merged ); free( fstart );
+  if ( !opts.relax ) {
+    for ( int s = 0; s < nf; s++ ) sn_start[ns++] = fstart[s];
+    sn_start[ns] = n;
+  } else {
+    int* col2f = malloc( sizeof( int ) * n );
+    for ( int s = 0; s < nf; s++ ) for ( int j = fstart[s]; j < fstart[s + 1]; j++ ) col2f[j] = s;
+    int* fpar = malloc( sizeof( int ) * nf );
+    for ( int s = 0; s < nf; s++ ) { int p = parent[fstart[s + 1] - 1]; fpar[s] = p < 0 ? -1 : col2f[p]; }
+    double* gk = malloc( sizeof( double ) * nf ); double* gf = malloc( sizeof( double ) * nf ); double* gz = malloc( sizeof( double ) * nf );
+    int* into = malloc( sizeof( int ) * nf );        /* into[c] = supernode that absorbed c, -1 if none */
+    int* head = malloc( sizeof( int ) * nf ); int* tail = malloc( sizeof( int ) * nf ); int* nxt = malloc( sizeof( int ) * nf );
+    for ( int s = 0; s < nf; s++ ) { gk[s] = fstart[s + 1] - fstart[s]; gf[s] = cc[fstart[s]]; gz[s] = 0; into[s] = -1; head[s] = tail[s] = -1; nxt[s] = -1; }
+    for ( int s = 0; s < nf; s++ ) { int p = fpar[s]; if ( p >= 0 ) { if ( head[p] < 0 ) head[p] = s; else nxt[tail[p]] = s; tail[p] = s; } }
+    int* kids = malloc( sizeof( int ) * nf ); int nk;
+    for ( int p = 0; p < nf; p++ ) {
+      nk = 0;
+      for ( int c = head[p]; c != -1; c = nxt[c] ) kids[nk++] = c;
+      if ( nk == 0 ) continue;
+      /* largest front first: the chain child is tried before the small siblings (insertion sort, lists are short) */
+      for ( int a = 1; a < nk; a++ ) { int v = kids[a], q = a - 1; while ( q >= 0 && gf[kids[q]] < gf[v] ) { kids[q + 1] = kids[q]; q--; } kids[q + 1] = v; }
+      int nh = -1, nt = -1;   /* new child list of p */
+      for ( int a = 0; a < nk; a++ ) {
+        const int c = kids[a];
+        const double kc = gk[c], fc = gf[c], zc = gz[c], kp = gk[p], fp = gf[p], zp = gz[p];
+        const double k = kc + kp, f = kc + fp;
+        const double tot = panel_nnz( k, f );
+        const double z = tot - ( panel_nnz( kc, fc ) - zc ) - ( panel_nnz( kp, fp ) - zp );
+        const double frac = z / tot;
+        int ok;
+        if ( f <= 64 ) ok = 1;
+        else if ( k <= opts.nrelax[0] ) ok = 1;
+        else if ( k <= opts.nrelax[1] ) ok = frac < opts.zrelax[0];
+        else if ( k <= opts.nrelax[2] ) ok = frac < opts.zrelax[1];
+        else ok = frac < opts.zrelax[2];
+        if ( ok ) {
+          into[c] = p; gk[p] = k; gf[p] = f; gz[p] = z;
+          if ( head[c] >= 0 ) { if ( nh < 0 ) nh = head[c]; else nxt[nt] = head[c]; nt = tail[c]; }   /* adopt the grandchildren */
+        } else { if ( nh < 0 ) nh = c; else nxt[nt] = c; nt = c; nxt[c] = -1; }
+      }
+      if ( nt >= 0 ) nxt[nt] = -1;
+      head[p] = nh; tail[p] = nt;
+    }
+    free( kids );
+    /* group root of every fundamental supernode */
+    int* root = malloc( sizeof( int ) * nf );
+    for ( int s = nf - 1; s >= 0; s-- ) root[s] = into[s] < 0 ? s : root[into[s]];
+    int* gid = malloc( sizeof( int ) * nf ); int ng = 0;
+    for ( int s = 0; s < nf; s++ ) if ( into[s] < 0 ) gid[s] = ng++;
+    int* gpar = malloc( sizeof( int ) * ( ng > 0 ? ng : 1 ) ); int* gkey = malloc( sizeof( int ) * ( ng > 0 ? ng : 1 ) ); int* gpost = malloc( sizeof( int ) * ( ng > 0 ? ng : 1 ) );
+    for ( int s = 0; s < nf; s++ ) if ( into[s] < 0 ) { gpar[gid[s]] = fpar[s] < 0 ? -1 : gid[root[fpar[s]]]; double f = gf[s]; gkey[gid[s]] = f > ng ? ng : ( int )f; }
+    postorder( ng, gpar, gkey, gpost );
+    /* members of each group in ascending (= topological) order */
+    int* mcnt = calloc( ng + 1, sizeof( int ) );
+    for ( int s = 0; s < nf; s++ ) mcnt[gid[root[s]] + 1]++;
+    for ( int g = 0; g < ng; g++ ) mcnt[g + 1] += mcnt[g];
+    int* mem = malloc( sizeof( int ) * nf );
+    { int* w = malloc( sizeof( int ) * ( ng + 1 ) ); memcpy( w, mcnt, sizeof( int ) * ( ng + 1 ) ); for ( int s = 0; s < nf; s++ ) mem[w[gid[root[s]]]++] = s; free( w ); }
+    /* new column order */
+    int* np = malloc( sizeof( int ) * n ); int pos = 0;
+    for ( int t = 0; t < ng; t++ ) {
+      const int g = gpost[t];
+      sn_start[ns++] = pos;
+      for ( int q = mcnt[g]; q < mcnt[g + 1]; q++ ) { const int fs = mem[q]; for ( int j = fstart[fs]; j < fstart[fs + 1]; j++ ) np[pos++] = S->perm[j]; }
+    }
+    sn_start[ns] = n;
+    memcpy( S->perm, np, sizeof( int ) * n ); free( np );
+    for ( int k = 0; k < n; k++ ) S->iperm[S->perm[k]] = k;
+    free( col2f ); free( fpar ); free( gk ); free( gf ); free( gz ); free( into ); free( head ); free( tail ); free( nxt );
+    free( root ); free( gid ); free( gpar ); free( gkey ); free( gpost ); free( mcnt ); free( mem );
+    /* the renumbering is a topological reordering: same fill, but the arrays must follow the new labels */
+    free( lp ); free( li ); free( up ); free( ui );
+    build_lower_pattern( n, cp, ri, kind, S->iperm, &lp, &li );
+    transpose_pattern( n, lp, li, &up, &ui );
+    b200_etree( n, up, ui, parent );
+    /* the new numbering is topological but not a postorder (siblings' subtrees interleave): give GNP one */
+    { int* post2 = malloc( sizeof( int ) * n ); postorder( n, parent, NULL, post2 ); colcounts_post( n, parent, post2, lp, li, cc ); free( post2 ); }
+  }
+  free( fstart );
   S->ns = ns; S->sn_start = realloc( sn_start, sizeof( int ) * ( ns + 1 ) );
   sn_start = S->sn_start;
   int* col2sn = malloc( sizeof( int ) * n );

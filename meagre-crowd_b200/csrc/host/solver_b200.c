@@ -11,7 +11,7 @@
  *   - errors: message on stderr + abort(), like the reference's assert()s
  *   - analyze/factorize/evaluate may be repeated on one state (-r N)
  * Tuning comes from the environment because the callbacks carry no options:
- *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_REFINE (steps, default 1), B200_VERBOSE.
+ *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_REFINE (steps; default automatic), B200_VERBOSE.
  * There is no CPU fallback: without a usable GPU, init aborts.
  */
 #include <assert.h>

@@ -27,6 +27,7 @@ def run(name, gen, kind, sym, p=1, profile=False):
     fl = S.flops * (2 if kind else 1)
     print(f"{name}: n={n} nnzL={S.nnzL:.3g} flops={fl:.3g} ns={S.ns} analyze={ta:.2f}s factor_wall={tf*1e3:.1f}ms dev={st.factor_ms:.1f}ms ({fl/st.factor_ms/1e9:.2f} TF/s) launches={st.launches} solve_wall={ts*1e3:.1f}ms dev={st2.solve_ms:.2f}ms launches={st2.solve_launches} berr={be:.2e}", flush=True)
     if profile:
+        x = s.solve(b)
         buf = (b"\0" * 4096); import ctypes as C
         cb = C.create_string_buffer(4096); s.L.b200_get_profile(s.ctx, cb, 4096); print(cb.value.decode())
     s.close()
