@@ -80,7 +80,8 @@ typedef struct b200_symbolic {
   int64_t* rowptr;       /* [ns+1] into rowidx                                     */
   int* rowidx;           /* front row lists, sorted; first k_s entries = pivots    */
   int* relidx;           /* same indexing; for i>=k_s: position in parent's front  */
-  int64_t* lptr;         /* [ns+1] panel offsets (f_s x k_s, column-major, ld f_s) */
+  int64_t* lptr;         /* [ns+1] panel offsets: f_s x k_s, column-major, leading dimension
+                            ld_s = f_s rounded up to even (16-byte aligned columns)  */
   int64_t* uptr;         /* [ns+1] LU only: offsets of the U' panels (same layout as L: uptr==lptr) */
   int64_t* amap;         /* [nnzA] destination of every stored input entry: offset
                             into L storage; for LU, entries of the strict upper
@@ -91,7 +92,8 @@ typedef struct b200_symbolic {
   int maxfront;          /* largest front order                                    */
   int maxdepth;          /* deepest level                                          */
   int64_t cb_arena[2];   /* doubles needed by the two contribution-block arenas    */
-  int64_t* cbptr;        /* [ns] offset of the contribution block in its arena     */
+  int64_t* cbptr;        /* [ns] offset of the contribution block in its arena (u_s x u_s,
+                            leading dimension u_s rounded up to even)               */
   int64_t* spmv_ptr;     /* [n+1] row pointers of the FULL matrix in the original numbering  */
   int* spmv_col;         /* column of each entry                                              */
   int* spmv_src;         /* index of its value in the input array (residual for refinement)   */
@@ -142,7 +144,7 @@ int b200_flush_l2( b200_ctx_t* c );             /* write a >L2 buffer between ti
 
 /* iterative refinement: r = b - A x is accumulated in double-double on the device, then one more
  * pair of sweeps corrects x.  steps >= 0: exactly that many; steps < 0 (default): automatic -- one
- * step for small systems (n*p <= 65536), otherwise only while the componentwise backward error
+ * step for small systems (n <= 65536), otherwise only while the componentwise backward error
  * max_i |r_i| / (|A||x|+|b|)_i is above 1e-15 (at most 2 steps) */
 int b200_set_refinement( b200_ctx_t* c, int steps );
 

@@ -233,6 +233,12 @@ def analyze(n, colptr, rowidx, kind=KIND_CHOLESKY, ordering=ORDER_ND, perm=None,
     return S
 
 
+def panel_view(flat, offset, f, k):
+    """f x k view of a factor panel: column-major, leading dimension f rounded up to even"""
+    ld = (int(f) + 1) & ~1
+    return flat[int(offset):int(offset) + ld * int(k)].reshape((ld, int(k)), order="F")[:int(f)]
+
+
 def sym_array(S, name, length, dtype):
     p = getattr(S.contents, name)
     ct = {np.int32: C.c_int, np.int64: C.c_int64}[dtype]
@@ -296,7 +302,7 @@ class Solver:
         for s in range(ns):
             k = st[s + 1] - st[s]; f = rp[s + 1] - rp[s]
             rows = ri[rp[s]:rp[s + 1]]
-            panel = flat[lp[s]:lp[s] + f * k].reshape((f, k), order="F")
+            panel = panel_view(flat, lp[s], f, k)
             Ld[np.ix_(rows, np.arange(st[s], st[s + 1]))] = panel
         return np.tril(Ld)
 

@@ -56,7 +56,7 @@ struct AsmTask { int parent; int col0; int ncols; };
 
 struct SnMeta {           /* per supernode, device copy */
   int64_t lptr, uptr, cbptr, rowptr, invptr;
-  int c0, k, f, parent, depth, child_begin, child_end, pad;
+  int c0, k, f, parent, depth, child_begin, child_end, ld;   /* ld: leading dimension of the panel (f rounded up to even) */
   int64_t wptr;           /* solve workspace row offset within its level arena */
 };
 
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
   const AsmTask t = tasks[blockIdx.x];
   const SnMeta P = sn[t.parent];
   const int kp = P.k, fp = P.f, up = fp - kp;
+  const int64_t ldp = P.ld, ldup = ( up + 1 ) & ~1;
   double* Lp = L + P.lptr;
   double* Up = LU ? U + P.uptr : nullptr;
   double* CBp = cb_parent + P.cbptr;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
     const SnMeta C = sn[child_list[ci]];
     const int uc = C.f - C.k;
     if ( uc == 0 ) continue;
+    const int64_t lduc = ( uc + 1 ) & ~1;
     const int* rel = relidx + C.rowptr + C.k;
     const double* src = cb_child + C.cbptr;
     /* range [a,b) of child columns whose destination column is in [lo,hi): rel is increasing */
@@ -127,14 +129,14 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
       /* a destination column belongs to exactly one warp, whichever child feeds it:
        * children can then be processed back to back without a barrier */
       if ( ( ( dj - lo ) & ( nwarps - 1 ) ) != warp ) continue;
-      const double* s = src + ( int64_t )j * uc;
+      const double* s = src + ( int64_t )j * lduc;
       if ( !LU ) {
         /* lower triangle only: i >= j, hence rel[i] >= dj */
         if ( dj < kp ) {
-          double* d = Lp + ( int64_t )dj * fp;
+          double* d = Lp + ( int64_t )dj * ldp;
           for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
         } else {
-          double* d = CBp + ( int64_t )( dj - kp ) * up - kp;
+          double* d = CBp + ( int64_t )( dj - kp ) * ldup - kp;
           for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
         }
       } else {
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
         for ( int i = lane; i < uc; i += 32 ) {
           const int di = rel[i];
           const double v = s[i];
-          if ( di >= dj ) { if ( dj < kp ) Lp[( int64_t )dj * fp + di] += v; else CBp[( int64_t )( dj - kp ) * up + ( di - kp )] += v; }
-          else { if ( di < kp ) Up[( int64_t )di * fp + dj] += v; else CBp[( int64_t )( dj - kp ) * up + ( di - kp )] += v; }
+          if ( di >= dj ) { if ( dj < kp ) Lp[( int64_t )dj * ldp + di] += v; else CBp[( int64_t )( dj - kp ) * ldup + ( di - kp )] += v; }
+          else { if ( di < kp ) Up[( int64_t )di * ldp + dj] += v; else CBp[( int64_t )( dj - kp ) * ldup + ( di - kp )] += v; }
         }
       }
     }
@@ -348,8 +350,11 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
   const double* Bg = t.B + n0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
-  const bool a16 = ( ( ( uintptr_t )Ag & 15 ) == 0 ) && ( ( t.lda & 1 ) == 0 );
-  const bool b16 = ( ( ( uintptr_t )Bg & 15 ) == 0 ) && ( ( t.ldb & 1 ) == 0 );
+  /* 16-byte cp.async needs 16-byte aligned sources.  Leading dimensions are even by construction; when
+   * the tile's first row sits at an odd offset the whole tile is fetched one row early (that row is
+   * valid memory of the same panel column and is never read back) and every fragment read is shifted. */
+  const bool a16 = ( t.lda & 1 ) == 0, b16 = ( t.ldb & 1 ) == 0;
+  const int sa = a16 ? ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ) : 0, sb = b16 ? ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 ) : 0;
   const int K = t.K;
   const int nk = ( K + BK - 1 ) / BK;
 
@@ -357,11 +362,12 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
     double* as = As + stage * BK * LDA;
     double* bs = Bs + stage * BK * LDB;
     if ( a16 ) {
-      for ( int c = tid; c < BK * BM / 2; c += NT ) {
-        const int q = c / ( BM / 2 ), r = ( c % ( BM / 2 ) ) * 2;
+      for ( int c = tid; c < BK * ( BM / 2 + 1 ); c += NT ) {
+        const int q = c / ( BM / 2 + 1 ), r2 = ( c % ( BM / 2 + 1 ) ) * 2, r = r2 - sa;   /* global row r, smem slot r2 */
+        if ( r2 >= BM + sa ) continue;
         const int kq = k0 + q;
-        int bytes = ( kq < K ) ? max( 0, min( 2, mrem - r ) ) * 8 : 0;
-        cp_async16( as + q * LDA + r, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
+        const int bytes = ( kq < K && r < mrem ) ? ( r + 1 < mrem ? 16 : 8 ) : 0;
+        cp_async16( as + q * LDA + r2, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
       }
     } else {
       for ( int c = tid; c < BK * BM; c += NT ) {
@@ -372,11 +378,12 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
       }
     }
     if ( b16 ) {
-      for ( int c = tid; c < BK * BN / 2; c += NT ) {
-        const int q = c / ( BN / 2 ), r = ( c % ( BN / 2 ) ) * 2;
+      for ( int c = tid; c < BK * ( BN / 2 + 1 ); c += NT ) {
+        const int q = c / ( BN / 2 + 1 ), r2 = ( c % ( BN / 2 + 1 ) ) * 2, r = r2 - sb;
+        if ( r2 >= BN + sb ) continue;
         const int kq = k0 + q;
-        int bytes = ( kq < K ) ? max( 0, min( 2, nrem - r ) ) * 8 : 0;
-        cp_async16( bs + q * LDB + r, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
+        const int bytes = ( kq < K && r < nrem ) ? ( r + 1 < nrem ? 16 : 8 ) : 0;
+        cp_async16( bs + q * LDB + r2, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
       }
     } else {
       for ( int c = tid; c < BK * BN; c += NT ) {
@@ -402,8 +409,8 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     { const int nx = kt + STAGES - 1; if ( nx < nk ) load_stage( nx % STAGES, nx * BK ); cp_async_commit(); }
-    const double* as = As + ( kt % STAGES ) * BK * LDA + wm0 + fr;
-    const double* bs = Bs + ( kt % STAGES ) * BK * LDB + wn0 + fr;
+    const double* as = As + ( kt % STAGES ) * BK * LDA + wm0 + fr + sa;
+    const double* bs = Bs + ( kt % STAGES ) * BK * LDB + wn0 + fr + sb;
 #pragma unroll
     for ( int kk = 0; kk < BK; kk += 4 ) {
       double af[MT], bf[NTL];
@@ -523,14 +530,14 @@ __global__ void __launch_bounds__( 256 ) fwd_block_kernel( const SolveBlk* __res
   if ( rt.r0 == 0 ) for ( int e = tid; e < nb * pcn; e += 256 ) { const int r = e % nb, q = e / nb; Z[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] = zs[r][q]; }
   const int lr = b.j0 + nb + rt.r0 + tid;   /* front-local row */
   if ( lr >= S.f ) return;
-  const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.f;
+  const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.ld;
   double acc[PC];
 #pragma unroll
   for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
   for ( int c0 = 0; c0 < nb; c0 += 16 ) {
     double lv[16];
 #pragma unroll
-    for ( int i = 0; i < 16; i++ ) lv[i] = ( c0 + i < nb ) ? Lr[( int64_t )( c0 + i ) * S.f] : 0.0;      /* 16 independent loads in flight */
+    for ( int i = 0; i < 16; i++ ) lv[i] = ( c0 + i < nb ) ? Lr[( int64_t )( c0 + i ) * S.ld] : 0.0;      /* 16 independent loads in flight */
 #pragma unroll
     for ( int i = 0; i < 16; i++ ) {
 #pragma unroll
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__( 256 ) bwd_block_kernel( const SolveBlk* __res
   }
   __syncthreads();
   for ( int c = warp; c < nb; c += 8 ) {
-    const double* col = M + S.lptr + base + ( int64_t )( b.j0 + c ) * S.f;
+    const double* col = M + S.lptr + base + ( int64_t )( b.j0 + c ) * S.ld;
     double lv[BWD_ROWS / 32];
 #pragma unroll
     for ( int i = 0; i < BWD_ROWS / 32; i++ ) { const int r = lane + 32 * i; lv[i] = r < rows ? col[r] : 0.0; }   /* 8 independent coalesced loads */

@@ -45,10 +45,12 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_THREADS = 256;
 constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 
-enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_COUNT };
-static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused" };
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_NOP, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused", "nop" };
 
-struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; };
+/* stream 0 = update stream (also level prologues), stream 1 = panel stream (look-ahead);
+ * wait_ev / record_ev index ctx->events (-1: none) */
+struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; int stream = 0; int wait_ev = -1; int record_ev = -1; };
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
@@ -70,7 +72,8 @@ template <class T> struct DevVec {
 
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  std::vector<cudaEvent_t> events; int nevents = 0;
   cudaDeviceProp prop;
   /* symbolic copy */
   int n = 0, ns = 0, kind = 0, maxdepth = 0;
@@ -120,7 +123,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   b200_ctx* c = new b200_ctx();
   c->device = device;
   CKN( cudaGetDeviceProperties( &c->prop, device ) );
-  CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+  CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
+    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); }
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
@@ -140,7 +144,7 @@ static void release_symbolic( b200_ctx* c ) {
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets );
   c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
-  c->launches.clear(); c->slaunches.clear();
+  c->launches.clear(); c->slaunches.clear(); c->nevents = 0;
   c->factored = false; c->device_bytes = 0;
 }
 
@@ -151,7 +155,8 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   release_symbolic( c );
   cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 );
-  cudaStreamDestroy( c->stream );
+  for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
+  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 );
   delete c;
 }
 
@@ -203,11 +208,11 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     SnMeta& m = meta[s];
     m.lptr = S->lptr[s]; m.uptr = S->uptr[s]; m.cbptr = S->cbptr[s]; m.rowptr = S->rowptr[s];
     m.c0 = S->sn_start[s]; m.k = S->sn_start[s + 1] - S->sn_start[s]; m.f = ( int )( S->rowptr[s + 1] - S->rowptr[s] );
-    m.parent = S->sn_parent[s]; m.depth = S->sn_depth[s]; m.child_begin = child_cnt[s]; m.child_end = child_cnt[s + 1]; m.pad = 0;
+    m.parent = S->sn_parent[s]; m.depth = S->sn_depth[s]; m.child_begin = child_cnt[s]; m.child_end = child_cnt[s + 1]; m.ld = ( m.f + 1 ) & ~1;
     m.invptr = invoff; invoff += ( int64_t )( m.k / NB ) * NB * NB + ( int64_t )( m.k % NB ) * ( m.k % NB );
     const int d = m.depth; const int64_t u = m.f - m.k;
     levels[d].push_back( s );
-    c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u * u + 1 ) & ~( int64_t )1 ) );
+    c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u + 1 ) & ~( int64_t )1 ) * u );
     m.wptr = c->level_w[d]; c->level_w[d] += u;
   }
   c->invsize = invoff;
@@ -258,15 +263,24 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     int maxk = 0, maxf = 0;
     for ( int s : lv ) { maxk = std::max( maxk, meta[s].k ); maxf = std::max( maxf, meta[s].f ); }
     const int NBO = outer_width( maxf );
+    /* look-ahead: with more than one outer panel, the next panel is factored on a second stream while
+     * the bulk of the trailing update of the current one still runs on the first */
+    const bool look = maxk > NBO;
+    int ev_next = -1;                       /* recorded after update_next(J-1): panel(J) may start */
+    if ( look ) {                           /* level prologue (and everything before it) done */
+      if ( LS.empty() || LS.back().record_ev >= 0 || LS.back().stream != 0 ) LS.push_back( { LK_NOP, 0, 0, d, 0.0 } );
+      LS.back().record_ev = c->nevents; ev_next = c->nevents++;
+    }
     for ( int J = 0; J < maxk; J += NBO ) {
+      const size_t panel_first = LS.size();
       for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
         const int64_t d0 = ( int64_t )dt.size();
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
           if ( j0 >= m.k ) continue;
           const int nb = std::min( NB, m.k - j0 );
-          DiagTask x; x.lda = m.f; x.nb = nb; x.col = m.c0 + j0;
-          x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.f; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.f : nullptr;
+          DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
+          x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
           x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
           x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
           dt.push_back( x );
@@ -283,12 +297,12 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           if ( below <= 0 ) continue;
           const double* inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB;
           const double* inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
-          TrsmTask x; x.B = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.f; x.ldb = m.f; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr;
+          TrsmTask x; x.B = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.ldb = m.ld; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr;
           int id = ( int )tt.size(); tt.push_back( x );
           for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
           tflops += ( double )below * nb * nb;
           if ( LU ) {
-            TrsmTask y; y.B = Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.f; y.ldb = m.f; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0;
+            TrsmTask y; y.B = Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0;
             id = ( int )tt.size(); tt.push_back( y );
             for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
             tflops += ( double )below * nb * nb;
@@ -306,10 +320,10 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           if ( jn >= jend ) continue;
           double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
           double fl = 0;
-          if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, 0 );
+          if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, 0 );
           else {
-            add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, Up + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, 0 );
-            add_gemm( gt, tb, ts, fl, Up + jn + ( int64_t )jn * m.f, m.f, Up + jn + ( int64_t )j0 * m.f, m.f, Lp + jn + ( int64_t )j0 * m.f, m.f, m.f - jn, jend - jn, nb, 1, -1 );
+            add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, Up + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, 0 );
+            add_gemm( gt, tb, ts, fl, Up + jn + ( int64_t )jn * m.ld, m.ld, Up + jn + ( int64_t )j0 * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, -1 );
           }
           fb += fl;
         }
@@ -318,35 +332,59 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( ( int64_t )ts.size() > s0 ) LS.push_back( { LK_GEMM_SMALL, s0, ( int64_t )ts.size() - s0, d, 0.0 } );
         if ( !LS.empty() && ( LS.back().kind == LK_GEMM_BIG || LS.back().kind == LK_GEMM_SMALL ) ) LS.back().flops += fb;
       }
-      /* trailing update with the whole outer panel: remaining pivot columns and the contribution block */
-      const int64_t b0 = ( int64_t )tb.size(), s0 = ( int64_t )ts.size();
-      double fl = 0;
-      for ( int s : lv ) {
-        const SnMeta& m = meta[s];
-        if ( J >= m.k ) continue;
-        const int kb = std::min( NBO, m.k - J ); const int Jn = J + kb; const int u = m.f - m.k;
-        double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
-        double* cb = CB + m.cbptr;
-        if ( !LU ) {
-          if ( Jn < m.k ) add_gemm( gt, tb, ts, fl, Lp + Jn + ( int64_t )Jn * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, 0 );
-          if ( u > 0 ) add_gemm( gt, tb, ts, fl, cb, u, Lp + m.k + ( int64_t )J * m.f, m.f, Lp + m.k + ( int64_t )J * m.f, m.f, u, u, kb, 1, 0 );
-        } else {
-          if ( Jn < m.k ) {
-            add_gemm( gt, tb, ts, fl, Lp + Jn + ( int64_t )Jn * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, Up + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, 0 );
-            add_gemm( gt, tb, ts, fl, Up + Jn + ( int64_t )Jn * m.f, m.f, Up + Jn + ( int64_t )J * m.f, m.f, Lp + Jn + ( int64_t )J * m.f, m.f, m.f - Jn, m.k - Jn, kb, 1, -1 );
+      int ev_panel = -1;
+      if ( look && LS.size() > panel_first ) {
+        for ( size_t q = panel_first; q < LS.size(); q++ ) LS[q].stream = 1;
+        LS[panel_first].wait_ev = ev_next;
+        LS.back().record_ev = c->nevents; ev_panel = c->nevents++;
+      }
+      /* trailing update with the whole outer panel, in two launches: first the columns of the NEXT
+       * outer panel (all the next panel factorization depends on), then the remaining pivot columns
+       * and the contribution block */
+      for ( int part = 0; part < 2; part++ ) {
+        const int64_t b0 = ( int64_t )tb.size();
+        double fl = 0;
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( J >= m.k ) continue;
+          const int kb = std::min( NBO, m.k - J ); const int Jn = J + kb; const int u = m.f - m.k;
+          const int Jn2 = std::min( m.k, Jn + NBO );           /* end of the next outer panel */
+          double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+          double* cb = CB + m.cbptr;
+          const int c_lo = part == 0 ? Jn : Jn2, c_hi = part == 0 ? Jn2 : m.k;   /* pivot columns updated by this part */
+          if ( c_lo < c_hi ) {
+            double* Cl = Lp + c_lo + ( int64_t )c_lo * m.ld; const double* Al = Lp + c_lo + ( int64_t )J * m.ld;
+            if ( !LU ) add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Al, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
+            else {
+              double* Cu = Up + c_lo + ( int64_t )c_lo * m.ld; const double* Au = Up + c_lo + ( int64_t )J * m.ld;
+              add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Au, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
+              add_gemm( gt, tb, ts, fl, Cu, m.ld, Au, m.ld, Al, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, -1 );
+            }
           }
-          if ( u > 0 ) add_gemm( gt, tb, ts, fl, cb, u, Lp + m.k + ( int64_t )J * m.f, m.f, Up + m.k + ( int64_t )J * m.f, m.f, u, u, kb, 0, 0 );
+          if ( part == 1 && u > 0 ) {
+            const double* Al = Lp + m.k + ( int64_t )J * m.ld;
+            if ( !LU ) add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Al, m.ld, u, u, kb, 1, 0 );
+            else add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Up + m.k + ( int64_t )J * m.ld, m.ld, u, u, kb, 0, 0 );
+          }
+        }
+        const bool any = ( int64_t )tb.size() > b0;
+        if ( any ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, fl } ); }
+        if ( look ) {
+          if ( part == 0 ) {
+            if ( !any ) LS.push_back( { LK_NOP, 0, 0, d, 0.0 } );
+            LS.back().wait_ev = ev_panel;                               /* update stream waits for the panel */
+            LS.back().record_ev = c->nevents; ev_next = c->nevents++;   /* next panel may start */
+          }
         }
       }
-      if ( ( int64_t )tb.size() > b0 ) LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } );
-      if ( ( int64_t )ts.size() > s0 ) LS.push_back( { LK_GEMM_SMALL, s0, ( int64_t )ts.size() - s0, d, 0.0 } );
-      if ( !LS.empty() && ( LS.back().kind == LK_GEMM_BIG || LS.back().kind == LK_GEMM_SMALL ) ) LS.back().flops += fl;
     }
+    if ( look ) { /* the level's last panel event is already waited on by its update; nothing left on stream 1 */ }
   }
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
 
   c->gemm_alg_flops = g_alg_flops;
+  while ( ( int )c->events.size() < c->nevents ) { cudaEvent_t e; CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) ); c->events.push_back( e ); }
   /* ---- solve schedule: forward deepest->root, backward root->deepest */
   std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<int> gp;
   std::vector<SLaunch>& SS = c->slaunches;
@@ -416,27 +454,34 @@ static int run_factor( b200_ctx* c ) {
   double gemm_flops = 0; int64_t gemm_launches = 0;
   for ( int k = 0; k < LK_COUNT; k++ ) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
   for ( const Launch& l : c->launches ) {
-    if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
+    cudaStream_t ls = l.stream ? c->stream2 : c->stream;
+    if ( l.wait_ev >= 0 ) CK( cudaStreamWaitEvent( ls, c->events[l.wait_ev], 0 ) );
+    if ( c->profile ) CK( cudaEventRecord( c->evp0, ls ) );
     switch ( l.kind ) {
-      case LK_MEMSET_CB: CK( cudaMemsetAsync( c->dCB[l.first], 0, ( size_t )l.count * 8, st ) ); break;
+      case LK_MEMSET_CB: CK( cudaMemsetAsync( c->dCB[l.first], 0, ( size_t )l.count * 8, ls ) ); break;
       case LK_ASM:
-        if ( LU ) extend_add_kernel<true><<<( unsigned )l.count, 256, 0, st>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
-        else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, st>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
+        if ( LU ) extend_add_kernel<true><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
+        else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
         break;
       case LK_DIAG:
-        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, st>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
-        else potrf_diag_kernel<<<( unsigned )l.count, 256, POTRF_SMEM, st>>>( c->diag_tasks.d + l.first, c->dErr );
+        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
+        else potrf_diag_kernel<<<( unsigned )l.count, 256, POTRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
-      case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, st>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
+      case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
       case LK_GEMM_BIG:
       case LK_GEMM_SMALL:
-        gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, st>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
+        gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
         gemm_flops += l.flops; gemm_launches++; break;
+      case LK_NOP: break;
     }
+    if ( l.record_ev >= 0 ) CK( cudaEventRecord( c->events[l.record_ev], ls ) );
     nlaunch++;
     if ( c->profile ) {
-      CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) );
+      CK( cudaEventRecord( c->evp1, ls ) ); CK( cudaEventSynchronize( c->evp1 ) );
       float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->prof_ms[l.kind] += ms; c->prof_n[l.kind]++;
+      static const bool trace = getenv( "B200_TRACE_GEMM" ) != nullptr;
+      if ( trace && ( l.kind == LK_GEMM_BIG || l.kind == LK_GEMM_SMALL ) && ms > 0.5f )
+        fprintf( stderr, "gemm depth=%d tiles=%lld flops=%.3e ms=%.3f TF/s=%.2f\n", l.depth, ( long long )l.count, l.flops, ms, l.flops / ( ms * 1e-3 ) / 1e12 );
     }
   }
   CK( cudaEventRecord( c->ev1, st ) );
@@ -557,7 +602,7 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
       CK( cudaStreamSynchronize( st ) );
       double omega; memcpy( &omega, &bits, sizeof( omega ) );
       c->stats.backward_error = omega;
-      const bool small = ( int64_t )n * p <= 65536;
+      const bool small = n <= 65536;     /* depends on n only: the answer must not depend on how columns are batched */
       if ( !( ( small && it == 0 ) || omega > 1e-15 ) ) break;
     }
     r = sweep_once( c, c->dR, p, c->dD, nl ); if ( r ) return r;

@@ -425,11 +425,12 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
   int64_t lo = 0, uo = 0; double sf = 0;
   for ( int s = 0; s < ns; s++ ) {
     int64_t k = sn_start[s + 1] - sn_start[s], f = S->rowptr[s + 1] - S->rowptr[s], u = f - k;
-    S->lptr[s] = lo; lo += f * k;
+    const int64_t ld = ( f + 1 ) & ~( int64_t )1, ldu = ( u + 1 ) & ~( int64_t )1;   /* even leading dimensions: 16-byte aligned columns */
+    S->lptr[s] = lo; lo += ld * k;
     S->uptr[s] = ( kind == B200_KIND_LU ) ? S->lptr[s] : 0; ( void )uo;
     sf += panel_flops( ( double )k, ( double )f );
     int d = S->sn_depth[s];
-    S->cbptr[s] = dsum[d]; dsum[d] += ( u * u + 1 ) & ~( int64_t )1; /* keep 16-byte alignment */
+    S->cbptr[s] = dsum[d]; dsum[d] += ldu * u;
   }
   S->lptr[ns] = lo; S->uptr[ns] = ( kind == B200_KIND_LU ) ? lo : 0; S->stored_nnzL = lo; S->stored_flops = sf;
   S->cb_arena[0] = S->cb_arena[1] = 0;
@@ -466,6 +467,7 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
       int s = col2sn[c];
       int c0 = sn_start[s], k = sn_start[s + 1] - c0;
       int64_t f = S->rowptr[s + 1] - S->rowptr[s];
+      const int64_t ld = ( f + 1 ) & ~( int64_t )1;
       int lr;
       if ( r < c0 + k ) lr = r - c0;
       else {
@@ -475,7 +477,7 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
         if ( lr < 0 ) { fprintf( stderr, "b200_analyze: internal error, row %d missing from front %d\n", r, s ); b200_symbolic_free( S ); free( col2sn ); return NULL; }
       }
       /* the L panel and (LU) the U' panel share one layout: column = pivot, row = front position */
-      S->amap[p] = S->lptr[s] + ( int64_t )( c - c0 ) * f + lr;
+      S->amap[p] = S->lptr[s] + ( int64_t )( c - c0 ) * ld + lr;
       if ( upper ) S->amap[p] |= ( int64_t )1 << 62;
     }
   }

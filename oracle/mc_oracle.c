@@ -278,7 +278,8 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
       }
       /* keep the panel, pass the contribution block up */
       double* P = Lpanels + lptr[s];
-      for ( int j = 0; j < k; j++ ) { memcpy( P + ( size_t )j * f + j, F + ( size_t )j * f + j, sizeof( double ) * ( f - j ) ); for ( int i = 0; i < j; i++ ) P[( size_t )j * f + i] = 0.0; }
+      const size_t ld = ( ( size_t )f + 1 ) & ~( size_t )1;   /* panels use an even leading dimension */
+      for ( int j = 0; j < k; j++ ) { memcpy( P + ( size_t )j * ld + j, F + ( size_t )j * f + j, sizeof( double ) * ( f - j ) ); for ( int i = 0; i < j; i++ ) P[( size_t )j * ld + i] = 0.0; }
       if ( u > 0 ) {
         double* C = malloc( sizeof( double ) * ( size_t )u * u );
         for ( int j = 0; j < u; j++ ) memcpy( C + ( size_t )j * u, F + ( size_t )( k + j ) * f + k, sizeof( double ) * u );
@@ -296,12 +297,12 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
 void oracle_mf_solve( int ns, const int* sn_start, const int64_t* rowptr, const int* rowidx, const int64_t* lptr, const double* Lpanels, double* x ) {
   for ( int s = 0; s < ns; s++ ) {
     const int c0 = sn_start[s], k = sn_start[s + 1] - c0, f = ( int )( rowptr[s + 1] - rowptr[s] );
-    const int* rows = rowidx + rowptr[s]; const double* P = Lpanels + lptr[s];
-    for ( int j = 0; j < k; j++ ) { const double v = x[c0 + j] / P[j + ( size_t )j * f]; x[c0 + j] = v; for ( int i = j + 1; i < f; i++ ) x[rows[i]] -= P[i + ( size_t )j * f] * v; }
+    const int* rows = rowidx + rowptr[s]; const double* P = Lpanels + lptr[s]; const size_t ld = ( ( size_t )f + 1 ) & ~( size_t )1;
+    for ( int j = 0; j < k; j++ ) { const double v = x[c0 + j] / P[j + ( size_t )j * ld]; x[c0 + j] = v; for ( int i = j + 1; i < f; i++ ) x[rows[i]] -= P[i + ( size_t )j * ld] * v; }
   }
   for ( int s = ns - 1; s >= 0; s-- ) {
     const int c0 = sn_start[s], k = sn_start[s + 1] - c0, f = ( int )( rowptr[s + 1] - rowptr[s] );
-    const int* rows = rowidx + rowptr[s]; const double* P = Lpanels + lptr[s];
-    for ( int j = k - 1; j >= 0; j-- ) { double v = x[c0 + j]; for ( int i = j + 1; i < f; i++ ) v -= P[i + ( size_t )j * f] * x[rows[i]]; x[c0 + j] = v / P[j + ( size_t )j * f]; }
+    const int* rows = rowidx + rowptr[s]; const double* P = Lpanels + lptr[s]; const size_t ld = ( ( size_t )f + 1 ) & ~( size_t )1;
+    for ( int j = k - 1; j >= 0; j-- ) { double v = x[c0 + j]; for ( int i = j + 1; i < f; i++ ) v -= P[i + ( size_t )j * ld] * x[rows[i]]; x[c0 + j] = v / P[j + ( size_t )j * ld]; }
   }
 }

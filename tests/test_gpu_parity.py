@@ -122,7 +122,7 @@ def test_cholesky_factor_and_solution_vs_oracle(mc, name, gen, relax):
     for sn in range(d["ns"]):
         c0, c1 = d["sn_start"][sn], d["sn_start"][sn + 1]
         rows = d["rowidx"][d["rowptr"][sn]:d["rowptr"][sn + 1]]; f = len(rows)
-        panel = flat[d["lptr"][sn]:d["lptr"][sn] + f * (c1 - c0)].reshape((f, c1 - c0), order="F")
+        panel = mc.panel_view(flat, d["lptr"][sn], f, c1 - c0)
         for j in range(c0, c1):
             col = np.zeros(n); col[rows[j - c0:]] = panel[j - c0:, j - c0]
             ref = np.zeros(n); ref[fac["Li"][fac["Lp"][j]:fac["Lp"][j + 1]]] = fac["Lx"][fac["Lp"][j]:fac["Lp"][j + 1]]
@@ -231,7 +231,7 @@ def test_headline_shape_properties_at_64cubed(mc):
     tr = 0.0
     for sn in range(d["ns"]):
         k = d["sn_start"][sn + 1] - d["sn_start"][sn]; f = d["rowptr"][sn + 1] - d["rowptr"][sn]
-        p = flat[d["lptr"][sn]:d["lptr"][sn] + f * k].reshape((f, k), order="F")
+        p = mc.panel_view(flat, d["lptr"][sn], f, k)
         tr += float((np.tril(p[:k]) ** 2).sum() + (p[k:] ** 2).sum())
     assert abs(tr - 6.0 * n) <= 1e-9 * 6.0 * n          # ||L||_F^2 = trace(A)
     s.close()

@@ -104,7 +104,7 @@ def test_front_structure_and_assembly_map(mc, name, gen, kind):
         else:
             assert f == k and d["sn_depth"][s] == 0
         # the assembly map reproduces P A P' inside the panel
-        panel = flatL[d["lptr"][s]:d["lptr"][s] + f * k].reshape((f, k), order="F")
+        panel = mc.panel_view(flatL, d["lptr"][s], f, k)
         ref = PA[np.ix_(rows, np.arange(c0, c1))].copy()
         if kind == 0:
             ref[:k, :] = np.tril(ref[:k, :])
@@ -112,7 +112,7 @@ def test_front_structure_and_assembly_map(mc, name, gen, kind):
         else:
             refl = ref.copy(); refl[:k, :] = np.tril(refl[:k, :])
             assert np.array_equal(panel, refl)
-            upanel = flatU[d["lptr"][s]:d["lptr"][s] + f * k].reshape((f, k), order="F")
+            upanel = mc.panel_view(flatU, d["lptr"][s], f, k)
             refu = PA[np.ix_(np.arange(c0, c1), rows)].T.copy(); refu[:k, :] = np.tril(refu[:k, :], -1)
             assert np.array_equal(upanel, refu)
     assert seen.all()
