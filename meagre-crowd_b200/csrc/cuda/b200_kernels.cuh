@@ -352,23 +352,45 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
   const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
   /* 16-byte cp.async needs 16-byte aligned sources.  Leading dimensions are even by construction; when
    * the tile's first row sits at an odd offset the whole tile is fetched one row early (that row is
-   * valid memory of the same panel column and is never read back) and every fragment read is shifted. */
+   * valid memory of the same panel column and is never read back) and every fragment read is shifted.
+   * Each thread owns a fixed set of 16-byte chunks: all address arithmetic happens once, before the
+   * K loop; per stage only the pointers advance (the issue slots belong to DMMA, not to IMAD). */
   const bool a16 = ( t.lda & 1 ) == 0, b16 = ( t.ldb & 1 ) == 0;
   const int sa = a16 ? ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ) : 0, sb = b16 ? ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 ) : 0;
   const int K = t.K;
   const int nk = ( K + BK - 1 ) / BK;
+  constexpr int TPC = NT / BK;                      /* threads per k-column                      */
+  constexpr int ACH = ( BM / 2 + TPC ) / TPC;       /* chunks per thread (incl. the shift chunk) */
+  constexpr int BCH = ( BN / 2 + TPC ) / TPC;
+  static_assert( NT % BK == 0, "threads must tile the k-columns" );
+  const int lq = tid / TPC, lc = tid % TPC;         /* my k-column inside a stage, my first chunk */
+  const double* gA[ACH]; int bA[ACH]; int oA[ACH];
+  const double* gB[BCH]; int bB[BCH]; int oB[BCH];
+#pragma unroll
+  for ( int j = 0; j < ACH; j++ ) {
+    const int r2 = 2 * ( lc + TPC * j ), r = r2 - sa;
+    const bool in = r2 < BM + 2 * sa;
+    bA[j] = !in ? -1 : ( r < mrem ) ? ( r + 1 < mrem ? 16 : 8 ) : 0;     /* -1: slot does not exist */
+    gA[j] = bA[j] > 0 ? Ag + r + ( int64_t )lq * t.lda : t.A;
+    oA[j] = lq * LDA + r2;
+  }
+#pragma unroll
+  for ( int j = 0; j < BCH; j++ ) {
+    const int r2 = 2 * ( lc + TPC * j ), r = r2 - sb;
+    const bool in = r2 < BN + 2 * sb;
+    bB[j] = !in ? -1 : ( r < nrem ) ? ( r + 1 < nrem ? 16 : 8 ) : 0;
+    gB[j] = bB[j] > 0 ? Bg + r + ( int64_t )lq * t.ldb : t.B;
+    oB[j] = lq * LDB + r2;
+  }
+  const int64_t stepA = ( int64_t )BK * t.lda, stepB = ( int64_t )BK * t.ldb;
 
   auto load_stage = [&]( int stage, int k0 ) {
     double* as = As + stage * BK * LDA;
     double* bs = Bs + stage * BK * LDB;
+    const bool kin = k0 + lq < K;
     if ( a16 ) {
-      for ( int c = tid; c < BK * ( BM / 2 + 1 ); c += NT ) {
-        const int q = c / ( BM / 2 + 1 ), r2 = ( c % ( BM / 2 + 1 ) ) * 2, r = r2 - sa;   /* global row r, smem slot r2 */
-        if ( r2 >= BM + sa ) continue;
-        const int kq = k0 + q;
-        const int bytes = ( kq < K && r < mrem ) ? ( r + 1 < mrem ? 16 : 8 ) : 0;
-        cp_async16( as + q * LDA + r2, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
-      }
+#pragma unroll
+      for ( int j = 0; j < ACH; j++ ) if ( bA[j] >= 0 ) { cp_async16( as + oA[j], gA[j], kin ? bA[j] : 0 ); if ( bA[j] > 0 ) gA[j] += stepA; }
     } else {
       for ( int c = tid; c < BK * BM; c += NT ) {
         const int q = c / BM, r = c % BM;
@@ -378,13 +400,8 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
       }
     }
     if ( b16 ) {
-      for ( int c = tid; c < BK * ( BN / 2 + 1 ); c += NT ) {
-        const int q = c / ( BN / 2 + 1 ), r2 = ( c % ( BN / 2 + 1 ) ) * 2, r = r2 - sb;
-        if ( r2 >= BN + sb ) continue;
-        const int kq = k0 + q;
-        const int bytes = ( kq < K && r < nrem ) ? ( r + 1 < nrem ? 16 : 8 ) : 0;
-        cp_async16( bs + q * LDB + r2, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
-      }
+#pragma unroll
+      for ( int j = 0; j < BCH; j++ ) if ( bB[j] >= 0 ) { cp_async16( bs + oB[j], gB[j], kin ? bB[j] : 0 ); if ( bB[j] > 0 ) gB[j] += stepB; }
     } else {
       for ( int c = tid; c < BK * BN; c += NT ) {
         const int q = c / BN, r = c % BN;
@@ -427,6 +444,136 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
   cp_async_wait<0>();
 
   /* epilogue: C -= acc (read-modify-write, masked to the stored triangle) */
+  double* Cg = t.C;
+#pragma unroll
+  for ( int j = 0; j < NTL; j++ ) {
+#pragma unroll
+    for ( int h = 0; h < 2; h++ ) {
+      const int c = n0 + wn0 + j * 8 + 2 * fk + h;
+      if ( c < t.N ) {
+        double* cc = Cg + ( int64_t )c * t.ldc;
+#pragma unroll
+        for ( int i = 0; i < MT; i++ ) {
+          const int r = m0 + wm0 + i * 8 + fr;
+          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) cc[r] -= acc[i][j][h];
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------- DMMA GEMM NT, bulk-copy pipeline
+ * Same product and the same shared-memory layout as gemm_nt_dmma_kernel, but the operand tiles are
+ * brought in by the async proxy: one elected producer thread issues, per stage, one
+ * cp.async.bulk (SASS UBLKCP) per k-column of A and of B -- each column of a panel tile is a contiguous
+ * run of <=66 doubles -- and the bytes are counted on an mbarrier.  The 8 consumer warps only ever wait
+ * on "full[stage]" and signal "empty[stage]": there is no block-wide barrier in the K loop, so a warp
+ * that gets ahead keeps the FP64 tensor pipe busy instead of waiting for the slowest one
+ * (ncu on the cp.async version: 13 % of all warp samples sat at the per-stage __syncthreads()).
+ * Requirements (true for every factor task): lda, ldb even; panel columns padded to their even ld. */
+__device__ __forceinline__ void mbar_init( uint64_t* bar, int count ) {
+  asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"( ( unsigned )__cvta_generic_to_shared( bar ) ), "r"( count ) );
+}
+__device__ __forceinline__ void mbar_expect_tx( uint64_t* bar, int bytes ) {
+  asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"( ( unsigned )__cvta_generic_to_shared( bar ) ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ void mbar_arrive( uint64_t* bar ) {
+  asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"( ( unsigned )__cvta_generic_to_shared( bar ) ) : "memory" );
+}
+__device__ __forceinline__ void mbar_wait( uint64_t* bar, int parity ) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"( ( unsigned )__cvta_generic_to_shared( bar ) ), "r"( parity ) : "memory" );
+}
+__device__ __forceinline__ void bulk_g2s( void* smem, const void* g, int bytes, uint64_t* bar ) {
+  asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"( ( unsigned )__cvta_generic_to_shared( smem ) ),
+                "l"( g ), "r"( bytes ), "r"( ( unsigned )__cvta_generic_to_shared( bar ) ) : "memory" );
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt_dmma_bulk_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles,
+                                                                                               const double* __restrict__ zeros ) {
+  constexpr int BK = 16;
+  constexpr int NCW = ( BM / WM ) * ( BN / WN );      /* consumer warps */
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  extern __shared__ double sm[];
+  double* As = sm;
+  double* Bs = sm + STAGES * BK * LDA;
+  uint64_t* full = reinterpret_cast<uint64_t*>( sm + STAGES * BK * ( LDA + LDB ) );
+  uint64_t* empty = full + STAGES;
+  const Tile tl = tiles[blockIdx.x];
+  const GemmTask t = tasks[tl.task];
+  const int m0 = tl.tm * BM, n0 = tl.tn * BN;
+  const int mrem = t.M - m0, nrem = t.N - n0;
+  const double* Ag = t.A + m0;
+  const double* Bg = t.B + n0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sa = ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ), sb = ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 );
+  const int K = t.K, nk = ( K + BK - 1 ) / BK;
+  if ( tid == 0 ) {
+    for ( int s = 0; s < STAGES; s++ ) { mbar_init( &full[s], 1 ); mbar_init( &empty[s], NCW ); }
+    asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
+    asm volatile( "fence.proxy.async.shared::cta;\n" ::: "memory" );
+  }
+  __syncthreads();
+
+  if ( warp == NCW ) {
+    /* ---------------- producer warp: lane l issues the copy of k-column l%16 of A (l<16) or B (l>=16),
+     * so a whole stage (32 columns) goes out with one warp instruction */
+    static_assert( BK == 16, "one lane per k-column of A and of B" );
+    const int ra = ( ( min( BM, mrem ) + sa + 1 ) & ~1 ) * 8, rb = ( ( min( BN, nrem ) + sb + 1 ) & ~1 ) * 8;   /* bytes per k-column */
+    const int q = lane & 15; const bool isb = lane >= 16;
+    const double* g = isb ? Bg - sb : Ag - sa;
+    const int64_t ldg = isb ? t.ldb : t.lda;
+    const int bytes = isb ? rb : ra;
+    for ( int kt = 0; kt < nk; kt++ ) {
+      const int slot = kt % STAGES, use = kt / STAGES;
+      if ( lane == 0 ) {
+        if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 );
+        mbar_expect_tx( &full[slot], BK * ( ra + rb ) );
+      }
+      __syncwarp();
+      double* dst = isb ? Bs + slot * BK * LDB + q * LDB : As + slot * BK * LDA + q * LDA;
+      const int kq = kt * BK + q;
+      /* K tail: feed zeros so that the partial k-step adds nothing */
+      bulk_g2s( dst, kq < K ? ( const void* )( g + ( int64_t )kq * ldg ) : ( const void* )zeros, bytes, &full[slot] );
+    }
+    return;
+  }
+
+  /* ---------------- consumers */
+  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
+  double acc[MT][NTL][2];
+#pragma unroll
+  for ( int i = 0; i < MT; i++ )
+#pragma unroll
+    for ( int j = 0; j < NTL; j++ ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const int fr = lane >> 2, fk = lane & 3;
+  for ( int kt = 0; kt < nk; kt++ ) {
+    const int slot = kt % STAGES;
+    mbar_wait( &full[slot], ( kt / STAGES ) & 1 );
+    const double* as = As + slot * BK * LDA + wm0 + fr + sa;
+    const double* bs = Bs + slot * BK * LDB + wn0 + fr + sb;
+#pragma unroll
+    for ( int kk = 0; kk < BK; kk += 4 ) {
+      double af[MT], bf[NTL];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
+#pragma unroll
+      for ( int j = 0; j < NTL; j++ ) bf[j] = bs[( kk + fk ) * LDB + j * 8];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ )
+#pragma unroll
+        for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
+    }
+    __syncwarp();
+    if ( lane == 0 ) mbar_arrive( &empty[slot] );     /* this warp is done reading the slot */
+  }
   double* Cg = t.C;
 #pragma unroll
   for ( int j = 0; j < NTL; j++ ) {

@@ -44,6 +44,8 @@ constexpr int GEMM_STAGES = 4;
 #define GEMM_CFG 64, 64, 32, 16, GEMM_STAGES
 constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_THREADS = 256;
 constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
+constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
+constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 
 enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_NOP, LK_COUNT };
 static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused", "nop" };
@@ -85,7 +87,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -128,6 +130,9 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
+  CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
+  CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
+  c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM ) );
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
@@ -153,7 +158,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   cudaSetDevice( c->device );
   cudaStreamSynchronize( c->stream );
   release_symbolic( c );
-  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); if ( c->flush_buf ) cudaFree( c->flush_buf );
+  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
   cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 );
@@ -470,7 +475,8 @@ static int run_factor( b200_ctx* c ) {
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
       case LK_GEMM_BIG:
       case LK_GEMM_SMALL:
-        gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
+        if ( c->use_bulk ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
+        else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
         gemm_flops += l.flops; gemm_launches++; break;
       case LK_NOP: break;
     }
@@ -702,7 +708,10 @@ extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, i
   float best = 1e30f;
   for ( int it = 0; it < iters + 2; it++ ) {
     cudaEventRecord( c->ev0, c->stream );
-    if ( dtb.n ) gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )dtb.n, GEMM_THREADS, BIG_SMEM, c->stream>>>( dgt.d, dtb.d );
+    if ( dtb.n ) {
+      if ( c->use_bulk && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )dtb.n, BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, c->dZeros );
+      else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )dtb.n, GEMM_THREADS, BIG_SMEM, c->stream>>>( dgt.d, dtb.d );
+    }
     cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
     float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
   }
