@@ -58,9 +58,9 @@ struct SnMeta {           /* per supernode, device copy */
   int64_t lptr, uptr, cbptr, rowptr, invptr;
   int c0, k, f, parent, depth, child_begin, child_end, ld;   /* ld: leading dimension of the panel (f rounded up to even) */
   int64_t wptr;           /* solve workspace row offset within its level arena */
+  int64_t sinv;           /* offset of its solve-block inverses (ceil(k/SB) blocks, nb x nb each) */
 };
 
-struct SolveBlk { int sn; int j0; int nb; int first_partial; int ntiles; int pad; };
 
 /* ---------------------------------------------------------- small helpers */
 __device__ __forceinline__ void cp_async8( void* smem, const void* g, int src_bytes ) {
@@ -606,17 +606,27 @@ __global__ void permute_out_kernel( const double* __restrict__ y, const int* __r
   for ( ; e < tot; e += stride ) { int k = ( int )( e % n ); int64_t c = e / n; x[perm[k] + c * n] = y[e]; }
 }
 
-/* forward: add the children's update vectors into the parent's pivots (y) and update rows (w) */
-__global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const int* __restrict__ parents, const SnMeta* __restrict__ sn, const int* __restrict__ child_list,
+/* forward: add the children's update vectors into the parent's pivots (y) and update rows (w).
+ * One CTA per (parent, range of GATHER_ROWS destination rows): the rows of a child that land in the
+ * range are a contiguous run (relidx is increasing); children are visited in a fixed order. */
+constexpr int GATHER_ROWS = 2048;
+struct GatherTask { int parent; int lo; int hi; };
+__global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const GatherTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const int* __restrict__ child_list,
                                                             const int* __restrict__ relidx, double* __restrict__ y, int n, int p,
                                                             double* __restrict__ w_parent, int64_t ldw_parent, const double* __restrict__ w_child, int64_t ldw_child ) {
-  const SnMeta P = sn[parents[blockIdx.x]];
+  const GatherTask t = tasks[blockIdx.x];
+  const SnMeta P = sn[t.parent];
   const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
   for ( int ci = P.child_begin; ci < P.child_end; ci++ ) {
     const SnMeta C = sn[child_list[ci]];
     const int uc = C.f - C.k;
     const int* rel = relidx + C.rowptr + C.k;
-    for ( int i = threadIdx.x; i < uc; i += blockDim.x ) {
+    int a = 0, b = uc;
+    if ( t.lo > 0 || t.hi < P.f ) {
+      { int x = 0, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.lo ) x = m + 1; else z = m; } a = x; }
+      { int x = a, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.hi ) x = m + 1; else z = m; } b = x; }
+    }
+    for ( int i = a + threadIdx.x; i < b; i += blockDim.x ) {
       const int d = rel[i];
       for ( int q = 0; q < pcn; q++ ) {
         const double v = w_child[C.wptr + i + ( int64_t )( pc0 + q ) * ldw_child];
@@ -628,181 +638,363 @@ __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const int* __restric
   }
 }
 
-/* Forward sweep, one launch per 64-column block step of a tree level.
- * Every CTA of a block first forms z = T * P * y_b in shared memory (T = inverse of the block's
- * triangular factor, 32 KB from L2; recomputing it per CTA removes a separate launch from the
- * dependency chain), then updates its 256 rows below the block: y/w -= L[rows, block] * z.
- * The CTA of the first tile also stores z (the finished forward values) into Z. */
-__global__ void __launch_bounds__( 256 ) fwd_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                           const double* __restrict__ L, const double* __restrict__ inv, const int* __restrict__ piv,
-                                                           double* __restrict__ y, double* __restrict__ Z, int n, int p, double* __restrict__ w, int64_t ldw ) {
-  __shared__ double ys[NB][PC];
-  __shared__ double zs[NB][PC];
-  const RowTile rt = tiles[blockIdx.x];
-  const SolveBlk b = blks[rt.task];
-  const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int nb = b.nb, tid = threadIdx.x;
-  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
-  for ( int e = tid; e < NB * PC; e += 256 ) { const int r = e / PC, q = e % PC; ys[r][q] = ( r < nb && q < pcn ) ? y[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] : 0.0; }
-  __syncthreads();
-  if ( piv ) {
-    if ( tid < pcn ) { const int* pv = piv + S.c0 + b.j0; for ( int j = 0; j < nb; j++ ) { const int pj = pv[j]; if ( pj != j ) { const double t = ys[j][tid]; ys[j][tid] = ys[pj][tid]; ys[pj][tid] = t; } } }
-    __syncthreads();
-  }
-  {
-    const int r = tid >> 2, part = tid & 3;
-    double acc[PC];
+/* ---- sweeps over SB-column pivot blocks ------------------------------------------------------
+ * A supernode's k pivot columns are cut into solve blocks of SB = 256 columns.  For every block
+ * the factorization leaves behind the explicit inverse of its triangular diagonal block
+ * (build_sinv_kernel), so one sweep step per block is
+ *     forward :  z_b = X_b y_b ;  y[rows below] -= L[rows below, b] z_b
+ *     backward:  x[cols before] -= L[rows of b, cols before]' x_b ;  x_{b-1} = X_{b-1}' (...)
+ * Both are streaming passes over a slab of the panel and are spread over many CTAs.  The small
+ * triangular product that produces the NEXT block's z (or x) is done by the last CTA to finish
+ * among the few tiles that own that block's rows (columns) -- an atomic ticket, no spinning --
+ * while the other CTAs of the launch are still streaming.  One launch per step and tree level. */
+constexpr int SB = 256;        /* solve block width (= threads per CTA)   */
+constexpr int FT_ROWS = 64;    /* rows per forward tile                   */
+constexpr int BT_COLS = 32;    /* columns per backward tile (4 per warp)  */
+constexpr int BWD_CH = 512;    /* rows staged in shared memory per pass   */
+
+struct SolveBlk {
+  int sn;
+  int j0, nb;          /* fwd: pivot block [j0,j0+nb) whose z multiplies the rows below it.
+                          bwd: front rows [j0,j0+nb) whose x feeds the columns before min(j0,k) */
+  int la_j0, la_nb;    /* look-ahead pivot block finished by its la_tiles tiles (la_nb = 0: none) */
+  int la_tiles;
+  int64_t la_inv;      /* offset of that block's solve inverse */
+  int64_t la_part;     /* offset (rows) of its la_tiles x la_nb partial products in the scratch buffer */
+};
+
+/* The triangular product that finishes the look-ahead block, out = M v (M = X forward, X' backward; nb <= SB),
+ * is split by COLUMN chunks of M: the tile that has just produced chunk j of v (64 values forward, 32 backward)
+ * multiplies its own columns of M into a partial vector; the last tile to arrive (atomic ticket, no spinning)
+ * adds the partial vectors in chunk order -- a fixed order, so the result does not depend on timing.
+ * vs: the chunk's values in shared memory, [CW][PCT].  Returns after the last tile has written out[]. */
+template <int PCT, int CW, bool FWD>
+__device__ __forceinline__ void la_finish( const double* __restrict__ Minv, int nb, int j, int nch, const double ( *vs )[PCT], double* __restrict__ part, int64_t part_row0,
+                                           double* out, int64_t ldo, int p, int pc0, int pcn, unsigned int* tk, int* is_last ) {
+  const int tid = threadIdx.x;
+  const int c0 = j * CW, cw = min( CW, nb - c0 );
+  /* rows of M that are non-zero in these columns: forward (lower) r >= c0 rounded down to its 64-block;
+   * backward (upper) r < end of the 64-block holding the chunk's last column */
+  const int r_lo = FWD ? ( c0 & ~63 ) : 0, r_hi = FWD ? nb : min( nb, ( ( c0 + cw - 1 ) | 63 ) + 1 );
+  if ( nch > 1 ) {
+    if ( tid >= r_lo && tid < r_hi ) {
+      double acc[PCT];
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-    {
-      double tv[NB / 4];
+      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+      const double* Mr = Minv + tid + ( int64_t )c0 * nb;
+      for ( int c = 0; c < cw; c += 16 ) {
+        double mv[16];
 #pragma unroll
-      for ( int i = 0; i < NB / 4; i++ ) { const int c = part + 4 * i; tv[i] = ( r < nb && c <= r ) ? __ldg( T + r + c * nb ) : 0.0; }   /* 16 independent loads in flight */
+        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < cw ) ? __ldg( Mr + ( int64_t )( c + i ) * nb ) : 0.0;
 #pragma unroll
-      for ( int i = 0; i < NB / 4; i++ ) {
-        const int c = part + 4 * i;
+        for ( int i = 0; i < 16; i++ ) {
+          const int ci = min( c + i, cw - 1 );
 #pragma unroll
-        for ( int q = 0; q < PC; q++ ) acc[q] += tv[i] * ys[c][q];
+          for ( int q = 0; q < PCT; q++ ) acc[q] += mv[i] * vs[ci][q];
+        }
       }
+      double* pr = part + ( part_row0 + ( int64_t )j * nb + tid ) * p + pc0;
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) pr[q] = acc[q];
     }
+    __threadfence();
+    __syncthreads();
+    if ( tid == 0 ) {
+      const unsigned int old = atomicAdd( tk, 1u );
+      *is_last = ( old == ( unsigned int )( nch - 1 ) );
+      if ( *is_last ) *tk = 0u;
+    }
+    __syncthreads();
+    if ( !*is_last ) return;
+    __threadfence();
+    if ( tid < nb ) {
+      const int j_lo = FWD ? 0 : ( tid & ~63 ) / CW, j_hi = FWD ? min( nch, ( ( tid | 63 ) + CW ) / CW ) : nch;
+      double acc[PCT];
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) { acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 1 ); acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 2 ); }
-    if ( part == 0 ) {
+      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+      for ( int jj = j_lo; jj < j_hi; jj++ ) {
+        const double* pr = part + ( part_row0 + ( int64_t )jj * nb + tid ) * p + pc0;
 #pragma unroll
-      for ( int q = 0; q < PC; q++ ) zs[r][q] = acc[q];
+        for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) acc[q] += __ldcg( pr + q );
+      }
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) out[tid + ( int64_t )q * ldo] = acc[q];
+    }
+  } else {
+    /* a single chunk: this tile finishes the block on its own */
+    if ( tid < nb ) {
+      double acc[PCT];
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+      const double* Mr = Minv + tid;
+      for ( int c = 0; c < cw; c += 16 ) {
+        double mv[16];
+#pragma unroll
+        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < cw ) ? __ldg( Mr + ( int64_t )( c + i ) * nb ) : 0.0;
+#pragma unroll
+        for ( int i = 0; i < 16; i++ ) {
+          const int ci = min( c + i, cw - 1 );
+#pragma unroll
+          for ( int q = 0; q < PCT; q++ ) acc[q] += mv[i] * vs[ci][q];
+        }
+      }
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) out[tid + ( int64_t )q * ldo] = acc[q];
     }
   }
-  __syncthreads();
-  if ( rt.r0 == 0 ) for ( int e = tid; e < nb * pcn; e += 256 ) { const int r = e % nb, q = e / nb; Z[S.c0 + b.j0 + r + ( int64_t )( pc0 + q ) * n] = zs[r][q]; }
-  const int lr = b.j0 + nb + rt.r0 + tid;   /* front-local row */
-  if ( lr >= S.f ) return;
-  const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.ld;
-  double acc[PC];
-#pragma unroll
-  for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-  for ( int c0 = 0; c0 < nb; c0 += 16 ) {
-    double lv[16];
-#pragma unroll
-    for ( int i = 0; i < 16; i++ ) lv[i] = ( c0 + i < nb ) ? Lr[( int64_t )( c0 + i ) * S.ld] : 0.0;      /* 16 independent loads in flight */
-#pragma unroll
-    for ( int i = 0; i < 16; i++ ) {
-#pragma unroll
-      for ( int q = 0; q < PC; q++ ) acc[q] += lv[i] * zs[( c0 + i ) & ( NB - 1 )][q];
-    }
-  }
-  if ( lr < S.k ) { for ( int q = 0; q < pcn; q++ ) y[S.c0 + lr + ( int64_t )( pc0 + q ) * n] -= acc[q]; }
-  else { for ( int q = 0; q < pcn; q++ ) w[S.wptr + ( lr - S.k ) + ( int64_t )( pc0 + q ) * ldw] -= acc[q]; }
 }
 
-/* Backward sweep, one launch per block step.  Each CTA reduces its 256 rows below the block:
- * partial[c] = sum_r M[row r, block col c] * x[row r]   (M = L panel: L' x; LU: the U' panel: U x),
- * warps own block columns, lanes stride over rows (coalesced).  The last CTA of a block to finish
- * (atomic ticket) sums the partials in tile order -- deterministic -- and forms
- * x_b = T' (z_b - sum) in place in Z. */
-constexpr int BWD_ROWS = 256;
-__global__ void __launch_bounds__( 256 ) bwd_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                           const double* __restrict__ M, const double* __restrict__ inv, const int* __restrict__ rowidx,
-                                                           double* __restrict__ x, int n, int p, double* __restrict__ partial, unsigned int* __restrict__ tickets ) {
-  __shared__ double xs[PC][BWD_ROWS];
-  __shared__ double rs[NB][PC + 1];
+/* z_0 = X_0 y_0 for the first block of every supernode of a level: one CTA per 64-column chunk of X_0 */
+template <int PCT>
+__global__ void __launch_bounds__( SB ) solve_first_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                                 const double* __restrict__ sinvF, const double* y, double* Z, int n, int p,
+                                                                 double* __restrict__ part, unsigned int* __restrict__ tickets ) {
+  __shared__ double ys[FT_ROWS][PCT];
   __shared__ int is_last;
   const RowTile rt = tiles[blockIdx.x];
   const SolveBlk b = blks[rt.task];
   const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
-  const int nb = b.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int base = b.j0 + nb + rt.r0;
-  const int rows = max( 0, min( BWD_ROWS, S.f - base ) );
-  const int tile_in_blk = rt.r0 / BWD_ROWS;
-  double* out = partial + ( ( int64_t )( b.first_partial + tile_in_blk ) * gridDim.y + blockIdx.y ) * NB * PC;
-  const int* ri = rowidx + S.rowptr;
-  for ( int e = tid; e < rows * pcn; e += 256 ) {
-    const int r = e % rows, q = e / rows;
-    const int lr = base + r;
-    const int g = lr < S.k ? S.c0 + lr : ri[lr];
-    xs[q][r] = x[g + ( int64_t )( pc0 + q ) * n];
-  }
+  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
+  const int j = rt.r0 / FT_ROWS, cw = min( FT_ROWS, b.la_nb - rt.r0 );
+  for ( int e = threadIdx.x; e < cw * PCT; e += SB ) { const int c = e % cw, q = e / cw; ys[c][q] = q < pcn ? y[S.c0 + b.la_j0 + rt.r0 + c + ( int64_t )( pc0 + q ) * n] : 0.0; }
   __syncthreads();
-  for ( int c = warp; c < nb; c += 8 ) {
-    const double* col = M + S.lptr + base + ( int64_t )( b.j0 + c ) * S.ld;
-    double lv[BWD_ROWS / 32];
+  la_finish<PCT, FT_ROWS, true>( sinvF + b.la_inv, b.la_nb, j, b.la_tiles, ys, part, b.la_part, Z + S.c0 + b.la_j0 + ( int64_t )pc0 * n, n, p, pc0, pcn,
+                                 tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
+}
+
+/* forward step: 64 rows x nb columns per CTA, thread = (row, column quarter) */
+template <int PCT>
+__global__ void __launch_bounds__( SB ) solve_fwd_step_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                              const double* __restrict__ L, const double* __restrict__ sinvF,
+                                                              double* y, double* Z, int n, int p, double* w, int64_t ldw, double* __restrict__ part, unsigned int* __restrict__ tickets ) {
+  __shared__ double zs[SB][PCT];
+  __shared__ double red[3][PCT][FT_ROWS];
+  __shared__ double ys[FT_ROWS][PCT];
+  __shared__ int is_last;
+  const RowTile rt = tiles[blockIdx.x];
+  const SolveBlk b = blks[rt.task];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
+  const int nb = b.nb, tid = threadIdx.x;
+  for ( int e = tid; e < nb * PCT; e += SB ) { const int c = e % nb, q = e / nb; zs[c][q] = q < pcn ? Z[S.c0 + b.j0 + c + ( int64_t )( pc0 + q ) * n] : 0.0; }
+  __syncthreads();
+  const int r = tid & ( FT_ROWS - 1 ), cq = tid >> 6;
+  const int lr = b.j0 + nb + rt.r0 + r;       /* front-local row */
+  double acc[PCT];
 #pragma unroll
-    for ( int i = 0; i < BWD_ROWS / 32; i++ ) { const int r = lane + 32 * i; lv[i] = r < rows ? col[r] : 0.0; }   /* 8 independent coalesced loads */
-    double acc[PC];
+  for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+  if ( lr < S.f ) {
+    const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.ld;
+    for ( int c = cq; c < nb; c += 64 ) {
+      double lv[16];
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
+      for ( int i = 0; i < 16; i++ ) lv[i] = ( c + 4 * i < nb ) ? Lr[( int64_t )( c + 4 * i ) * S.ld] : 0.0;      /* 16 independent coalesced loads */
 #pragma unroll
-    for ( int i = 0; i < BWD_ROWS / 32; i++ ) {
-      const int r = lane + 32 * i;
+      for ( int i = 0; i < 16; i++ ) {
+        const int ci = min( c + 4 * i, nb - 1 );     /* never touch uninitialised shared memory: 0 * NaN = NaN */
 #pragma unroll
-      for ( int q = 0; q < PC; q++ ) if ( q < pcn ) acc[q] += lv[i] * ( r < rows ? xs[q][r] : 0.0 );
+        for ( int q = 0; q < PCT; q++ ) acc[q] += lv[i] * zs[ci][q];
+      }
     }
+  }
+  if ( cq > 0 ) {
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) if ( q < pcn ) {
-        double v = acc[q];
-        for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
-        if ( lane == 0 ) out[c * PC + q] = v;
-      }
-  }
-  __threadfence();
-  __syncthreads();
-  if ( tid == 0 ) {
-    unsigned int* tk = tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y;
-    const unsigned int old = atomicAdd( tk, 1u );
-    is_last = ( old == ( unsigned int )( b.ntiles - 1 ) );
-    if ( is_last ) *tk = 0u;     /* ready for the next solve */
+    for ( int q = 0; q < PCT; q++ ) red[cq - 1][q][r] = acc[q];
   }
   __syncthreads();
-  if ( !is_last ) return;
-  __threadfence();
-  const double* T = inv + S.invptr + ( int64_t )( b.j0 / NB ) * NB * NB;
-  double* xb = x + S.c0 + b.j0;
-  {
-    /* sum the tiles' partials: four thread groups take tiles t = g, g+4, ...; combined in a fixed order */
-    double* ps = &xs[0][0];                         /* reuse: [4][NB*PC] */
-    const int g = tid >> 6, e0 = tid & 63;
-    for ( int e = e0; e < nb * pcn; e += 64 ) {
-      const int r = e % nb, q = e / nb;
-      const double* pp = partial + ( ( int64_t )b.first_partial * gridDim.y + blockIdx.y ) * NB * PC + r * PC + q;
-      double v = 0.0;
-      int t = g;
-      for ( ; t + 12 < b.ntiles; t += 16 ) {
-        const double a0 = __ldcg( pp + ( int64_t )t * gridDim.y * NB * PC ), a1 = __ldcg( pp + ( int64_t )( t + 4 ) * gridDim.y * NB * PC ),
-                     a2 = __ldcg( pp + ( int64_t )( t + 8 ) * gridDim.y * NB * PC ), a3 = __ldcg( pp + ( int64_t )( t + 12 ) * gridDim.y * NB * PC );
-        v += a0; v += a1; v += a2; v += a3;
+  const bool la = b.la_nb > 0 && rt.r0 < b.la_tiles * FT_ROWS;      /* this tile owns rows of the next pivot block */
+  if ( cq == 0 ) {
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) {
+      double yn = 0.0;
+      if ( q < pcn && lr < S.f ) {
+        const double v = ( ( acc[q] + red[0][q][r] ) + red[1][q][r] ) + red[2][q][r];
+        if ( lr < S.k ) { double* yp = y + S.c0 + lr + ( int64_t )( pc0 + q ) * n; yn = *yp - v; *yp = yn; }
+        else w[S.wptr + ( lr - S.k ) + ( int64_t )( pc0 + q ) * ldw] -= v;
       }
-      for ( ; t < b.ntiles; t += 4 ) v += __ldcg( pp + ( int64_t )t * gridDim.y * NB * PC );
-      ps[g * NB * PC + r * PC + q] = v;
+      if ( la ) ys[r][q] = yn;
+    }
+  }
+  if ( !la ) return;
+  __syncthreads();
+  la_finish<PCT, FT_ROWS, true>( sinvF + b.la_inv, b.la_nb, rt.r0 / FT_ROWS, b.la_tiles, ys, part, b.la_part, Z + S.c0 + b.la_j0 + ( int64_t )pc0 * n, n, p, pc0, pcn,
+                                 tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
+}
+
+/* backward step: x[c] -= sum_r M[r, c] x[r] for 32 columns per CTA (4 per warp; lanes run down the rows,
+ * coalesced) over the rows [j0, j0+nb) of the front: either a pivot block whose x has just been finished,
+ * or the update rows below the pivots (x gathered through the row list).  M = L panel (L' x) or U' panel (U x). */
+template <int PCT>
+__global__ void __launch_bounds__( SB ) solve_bwd_step_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
+                                                              const double* __restrict__ M, const double* __restrict__ sinvB, const int* __restrict__ rowidx,
+                                                              double* x, int n, int p, double* __restrict__ part, unsigned int* __restrict__ tickets ) {
+  __shared__ double xs[PCT][BWD_CH];      /* [rhs][row]: lanes read consecutive rows, no bank conflicts */
+  __shared__ double vn[BT_COLS][PCT];
+  __shared__ int is_last;
+  const RowTile rt = tiles[blockIdx.x];
+  const SolveBlk b = blks[rt.task];
+  const SnMeta S = sn[b.sn];
+  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool gather = b.j0 >= S.k;
+  const int climit = min( b.j0, S.k );
+  const int cbase = rt.r0 + warp * 4;
+  const int* ri = rowidx + S.rowptr;
+  double acc[4][PCT];
+#pragma unroll
+  for ( int j = 0; j < 4; j++ )
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) acc[j][q] = 0.0;
+  for ( int rc = 0; rc < b.nb; rc += BWD_CH ) {
+    const int rows = min( BWD_CH, b.nb - rc );
+    __syncthreads();
+    for ( int e = tid; e < rows * PCT; e += SB ) {
+      const int r = e % rows, q = e / rows;
+      const int lr = b.j0 + rc + r;
+      const int g = gather ? ri[lr] : S.c0 + lr;
+      xs[q][r] = q < pcn ? x[g + ( int64_t )( pc0 + q ) * n] : 0.0;
     }
     __syncthreads();
-    for ( int e = tid; e < NB * pcn; e += 256 ) {
-      const int r = e % NB, q = e / NB;
-      if ( r >= nb ) { rs[r][q] = 0.0; continue; }
-      const double sum = ( ( ps[r * PC + q] + ps[NB * PC + r * PC + q] ) + ps[2 * NB * PC + r * PC + q] ) + ps[3 * NB * PC + r * PC + q];
-      rs[r][q] = xb[r + ( int64_t )( pc0 + q ) * n] - sum;
+#pragma unroll
+    for ( int j = 0; j < 4; j++ ) {
+      if ( cbase + j >= climit ) continue;
+      const double* col = M + S.lptr + ( b.j0 + rc ) + ( int64_t )( cbase + j ) * S.ld;
+      for ( int r = lane; r < rows; r += 256 ) {
+        double lv[8];
+#pragma unroll
+        for ( int i = 0; i < 8; i++ ) lv[i] = ( r + 32 * i < rows ) ? col[r + 32 * i] : 0.0;
+#pragma unroll
+        for ( int i = 0; i < 8; i++ ) {
+          const int ri2 = min( r + 32 * i, rows - 1 );
+#pragma unroll
+          for ( int q = 0; q < PCT; q++ ) acc[j][q] += lv[i] * xs[q][ri2];
+        }
+      }
     }
   }
+  const bool la = b.la_nb > 0 && rt.r0 >= b.la_j0;        /* this tile owns columns of the pivot block that ends at climit */
+#pragma unroll
+  for ( int j = 0; j < 4; j++ ) {
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) {
+      double v = acc[j][q];
+      for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+      if ( lane == 0 ) {
+        double xn = 0.0;
+        if ( q < pcn && cbase + j < climit ) { double* xp = x + S.c0 + cbase + j + ( int64_t )( pc0 + q ) * n; xn = *xp - v; *xp = xn; }
+        if ( la ) vn[warp * 4 + j][q] = xn;
+      }
+    }
+  }
+  if ( !la ) return;
   __syncthreads();
-  {
-    const int r = tid >> 2, part = tid & 3;     /* x[r] = sum_{c>=r} T[c,r] rs[c] */
-    double acc[PC];
+  double* xb = x + S.c0 + b.la_j0 + ( int64_t )pc0 * n;
+  la_finish<PCT, BT_COLS, false>( sinvB + b.la_inv, b.la_nb, ( rt.r0 - b.la_j0 ) / BT_COLS, b.la_tiles, vn, part, b.la_part, xb, n, p, pc0, pcn,
+                                  tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
+}
+
+/* ---- explicit inverses of the SB-wide triangular diagonal blocks, from the panel and the 64x64 inverses the
+ * factorization already produced.  One CTA per (solve block, 64-column block column jb):
+ *   X_jj = T_j ;  X_ij = -T_i * sum_{q=jb}^{i-1} P_iq X_qj   (i > jb),   T_i = inv_i (* row interchanges of block i, LU)
+ * X goes out untransposed (forward sweep) and/or transposed (backward sweep). */
+struct SinvTask {
+  const double* P; int ld;      /* panel (L or U') of the supernode                     */
+  int j0, nb, jb;               /* solve block [j0, j0+nb), block column jb of it       */
+  const double* inv64;          /* 64x64 inverses of the supernode (block i at +i*4096) */
+  const int* piv;               /* LU: pivots of the supernode's columns (NULL: none)   */
+  double* X; double* XT;        /* nb x nb outputs, ld nb (XT may be NULL)              */
+};
+constexpr int SINV_SMEM = 3 * NB * ( NB + 1 ) * 8 + NB * 4;
+
+__global__ void __launch_bounds__( 256 ) build_sinv_kernel( const SinvTask* __restrict__ tasks ) {
+  extern __shared__ double dsm[];
+  double ( *As )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
+  double ( *Bs )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
+  double ( *Ts )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + 2 * NB * ( NB + 1 ) );
+  int* sig = reinterpret_cast<int*>( dsm + 3 * NB * ( NB + 1 ) );
+  const SinvTask t = tasks[blockIdx.x];
+  const int tid = threadIdx.x, nb = t.nb, jb = t.jb;
+  const int nsub = ( nb + NB - 1 ) / NB;
+  const int wj = min( NB, nb - NB * jb );
+  const int tr = ( tid & 15 ) * 4, tc = ( tid >> 4 ) * 4;
+  for ( int i = jb; i < nsub; i++ ) {
+    const int hi = min( NB, nb - NB * i );
+    /* T_i (with the block's interchanges folded in as a column permutation) */
+    __syncthreads();
+    if ( tid < NB ) sig[tid] = tid;
+    __syncthreads();
+    if ( t.piv && tid == 0 ) { const int* pv = t.piv + t.j0 + NB * i; for ( int j = 0; j < hi; j++ ) { const int pj = pv[j]; if ( pj != j ) { const int s = sig[j]; sig[j] = sig[pj]; sig[pj] = s; } } }
+    __syncthreads();
+    { const double* iv = t.inv64 + ( int64_t )( t.j0 / NB + i ) * NB * NB;
+      for ( int e = tid; e < NB * NB; e += 256 ) Ts[e % NB][e / NB] = 0.0;
+      __syncthreads();
+      for ( int e = tid; e < hi * hi; e += 256 ) { const int r = e % hi, c = e / hi; Ts[r][sig[c]] = iv[r + c * hi]; } }
+    __syncthreads();
+    double acc[4][4];
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) acc[q] = 0.0;
-    {
-      double tv[NB / 4];
+    for ( int a = 0; a < 4; a++ )
 #pragma unroll
-      for ( int i = 0; i < NB / 4; i++ ) { const int c = part + 4 * i; tv[i] = ( r < nb && c >= r && c < nb ) ? __ldg( T + c + r * nb ) : 0.0; }
+      for ( int c = 0; c < 4; c++ ) acc[a][c] = 0.0;
+    if ( i == jb ) {
 #pragma unroll
-      for ( int i = 0; i < NB / 4; i++ ) {
-        const int c = part + 4 * i;
+      for ( int a = 0; a < 4; a++ )
 #pragma unroll
-        for ( int q = 0; q < PC; q++ ) if ( q < pcn ) acc[q] += tv[i] * rs[c][q];
+        for ( int c = 0; c < 4; c++ ) acc[a][c] = Ts[tr + a][tc + c];
+    } else {
+      for ( int q = jb; q < i; q++ ) {
+        const int wq = min( NB, nb - NB * q );
+        __syncthreads();
+        for ( int e = tid; e < NB * NB; e += 256 ) {
+          const int r = e % NB, c = e / NB;
+          As[r][c] = ( r < hi && c < wq ) ? t.P[( t.j0 + NB * i + r ) + ( int64_t )( t.j0 + NB * q + c ) * t.ld] : 0.0;
+          Bs[r][c] = ( r < wq && c < wj ) ? t.X[( NB * q + r ) + ( int64_t )( NB * jb + c ) * nb] : 0.0;
+        }
+        __syncthreads();
+        for ( int kk = 0; kk < NB; kk++ ) {
+          double av[4], bv[4];
+#pragma unroll
+          for ( int a = 0; a < 4; a++ ) av[a] = As[tr + a][kk];
+#pragma unroll
+          for ( int c = 0; c < 4; c++ ) bv[c] = Bs[kk][tc + c];
+#pragma unroll
+          for ( int a = 0; a < 4; a++ )
+#pragma unroll
+            for ( int c = 0; c < 4; c++ ) acc[a][c] += av[a] * bv[c];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for ( int a = 0; a < 4; a++ )
+#pragma unroll
+        for ( int c = 0; c < 4; c++ ) { Bs[tr + a][tc + c] = acc[a][c]; acc[a][c] = 0.0; }
+      __syncthreads();
+      for ( int kk = 0; kk < NB; kk++ ) {
+        double av[4], bv[4];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ ) av[a] = Ts[tr + a][kk];
+#pragma unroll
+        for ( int c = 0; c < 4; c++ ) bv[c] = Bs[kk][tc + c];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ )
+#pragma unroll
+          for ( int c = 0; c < 4; c++ ) acc[a][c] -= av[a] * bv[c];
       }
     }
 #pragma unroll
-    for ( int q = 0; q < PC; q++ ) { acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 1 ); acc[q] += __shfl_xor_sync( 0xffffffffu, acc[q], 2 ); }
-    if ( part == 0 && r < nb ) for ( int q = 0; q < pcn; q++ ) xb[r + ( int64_t )( pc0 + q ) * n] = acc[q];
+    for ( int a = 0; a < 4; a++ )
+#pragma unroll
+      for ( int c = 0; c < 4; c++ ) {
+        const int r = tr + a, cc = tc + c;
+        if ( r < hi && cc < wj ) {
+          const int gr = NB * i + r, gc = NB * jb + cc;
+          t.X[gr + ( int64_t )gc * nb] = acc[a][c];
+          if ( t.XT ) t.XT[gc + ( int64_t )gr * nb] = acc[a][c];
+        }
+      }
+    /* blocks above the diagonal of this block column are zero */
+    if ( i == jb ) {
+      for ( int e = tid; e < NB * jb * wj; e += 256 ) { const int r = e % ( NB * jb ), c = e / ( NB * jb ); t.X[r + ( int64_t )( NB * jb + c ) * nb] = 0.0; if ( t.XT ) t.XT[( NB * jb + c ) + ( int64_t )r * nb] = 0.0; }
+    }
   }
 }
 

@@ -56,7 +56,7 @@ struct Launch { int kind; int64_t first; int64_t count; int depth; double flops;
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
-enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_BLOCK, SK_BWD_BLOCK, SK_COUNT };
+enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_FIRST, SK_FWD_STEP, SK_BWD_STEP, SK_COUNT };
 struct SLaunch { int kind; int64_t first; int64_t count; int64_t first_tile; int64_t ntiles; int depth; };
 
 template <class T> struct DevVec {
@@ -100,9 +100,12 @@ struct b200_ctx {
   /* solve */
   DevVec<SolveBlk> sblk; DevVec<RowTile> fwd_tiles, bwd_tiles; DevVec<int> gather_parents;
   std::vector<SLaunch> slaunches;
-  int64_t max_partial_tiles = 0, max_blocks_per_launch = 0;
+  int64_t max_blocks_per_launch = 0, sinvsize = 0, max_part_rows = 0;
+  double* dPart = nullptr; DevVec<GatherTask> gather_tasks;
   unsigned int* dTickets = nullptr; double* dZ = nullptr;
-  double *dY = nullptr, *dW[2] = { nullptr, nullptr }, *dPartial = nullptr, *dB = nullptr, *dX = nullptr;
+  double *dSinvF = nullptr, *dSinvB = nullptr, *dSinvTmp = nullptr;   /* solve-block inverses: X (forward), X' (backward) */
+  DevVec<SinvTask> sinv_tasks;
+  double *dY = nullptr, *dW[2] = { nullptr, nullptr }, *dB = nullptr, *dX = nullptr;
   int solve_p_cap = 0, io_p_cap = 0;
   void* flush_buf = nullptr; size_t flush_bytes = 0;
   bool factored = false;
@@ -136,19 +139,21 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM ) );
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
+  CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
   memset( &c->stats, 0, sizeof( c->stats ) );
   return c;
 }
 
 static void release_symbolic( b200_ctx* c ) {
   cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
+  cudaFree( c->dSinvF ); cudaFree( c->dSinvB ); cudaFree( c->dSinvTmp ); c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr; c->sinv_tasks.release();
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
   c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
   c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
-  c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release();
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets );
-  c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr;
-  c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
+  c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release(); c->gather_tasks.release();
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart );
+  c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->dPart = nullptr;
+  c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
   c->launches.clear(); c->slaunches.clear(); c->nevents = 0;
   c->factored = false; c->device_bytes = 0;
 }
@@ -208,25 +213,26 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   { std::vector<int> w( child_cnt.begin(), child_cnt.end() - 1 ); for ( int s = 0; s < ns; s++ ) if ( S->sn_parent[s] >= 0 ) child_list[w[S->sn_parent[s]]++] = s; }
   std::vector<std::vector<int>> levels( S->maxdepth + 1 );
   c->level_cb.assign( S->maxdepth + 1, 0 ); c->level_w.assign( S->maxdepth + 1, 0 );
-  int64_t invoff = 0;
+  int64_t invoff = 0, sinvoff = 0;
   for ( int s = 0; s < ns; s++ ) {
     SnMeta& m = meta[s];
     m.lptr = S->lptr[s]; m.uptr = S->uptr[s]; m.cbptr = S->cbptr[s]; m.rowptr = S->rowptr[s];
     m.c0 = S->sn_start[s]; m.k = S->sn_start[s + 1] - S->sn_start[s]; m.f = ( int )( S->rowptr[s + 1] - S->rowptr[s] );
     m.parent = S->sn_parent[s]; m.depth = S->sn_depth[s]; m.child_begin = child_cnt[s]; m.child_end = child_cnt[s + 1]; m.ld = ( m.f + 1 ) & ~1;
     m.invptr = invoff; invoff += ( int64_t )( m.k / NB ) * NB * NB + ( int64_t )( m.k % NB ) * ( m.k % NB );
+    m.sinv = sinvoff; sinvoff += ( int64_t )( m.k / SB ) * SB * SB + ( int64_t )( m.k % SB ) * ( m.k % SB );
     const int d = m.depth; const int64_t u = m.f - m.k;
     levels[d].push_back( s );
     c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u + 1 ) & ~( int64_t )1 ) * u );
     m.wptr = c->level_w[d]; c->level_w[d] += u;
   }
-  c->invsize = invoff;
+  c->invsize = invoff; c->sinvsize = sinvoff;
   c->w_rows[0] = c->w_rows[1] = 0;
   for ( int d = 0; d <= S->maxdepth; d++ ) c->w_rows[d & 1] = std::max( c->w_rows[d & 1], c->level_w[d] );
 
   /* ---- device storage */
   size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
-  const double need = ( double )c->lsize * 8.0 * ( LU ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 2 : 1 ) + ( double )S->nnzA * 16.0;
+  const double need = ( double )c->lsize * 8.0 * ( LU ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( LU ? 3 : 2 ) + ( double )S->nnzA * 16.0;
   if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
   CK( cudaMalloc( &c->dL, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
   if ( LU ) CK( cudaMalloc( &c->dU, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
@@ -234,6 +240,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   CK( cudaMalloc( &c->dInv, std::max<int64_t>( invoff, 1 ) * 8 ) );
   if ( LU ) { CK( cudaMalloc( &c->dInv2, std::max<int64_t>( invoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
+  CK( cudaMalloc( &c->dSinvF, std::max<int64_t>( sinvoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
+  if ( LU ) CK( cudaMalloc( &c->dSinvTmp, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
   c->device_bytes = ( int64_t )need;
   { std::vector<int64_t> v( S->amap, S->amap + S->nnzA ); if ( c->amap.upload( v ) ) return B200_ERR_CUDA; }
   { std::vector<int> v( S->perm, S->perm + n ); if ( c->perm.upload( v ) ) return B200_ERR_CUDA; }
@@ -390,52 +398,94 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
 
   c->gemm_alg_flops = g_alg_flops;
   while ( ( int )c->events.size() < c->nevents ) { cudaEvent_t e; CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) ); c->events.push_back( e ); }
-  /* ---- solve schedule: forward deepest->root, backward root->deepest */
-  std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<int> gp;
+  /* ---- solve-block inverses: one task per (solve block, 64-column block column) */
+  {
+    std::vector<SinvTask> sv;
+    for ( int s = 0; s < ns; s++ ) {
+      const SnMeta& m = meta[s];
+      for ( int j0 = 0; j0 < m.k; j0 += SB ) {
+        const int nb = std::min( SB, m.k - j0 );
+        const int64_t off = m.sinv + ( int64_t )( j0 / SB ) * SB * SB;
+        for ( int jb = 0; jb * NB < nb; jb++ ) {
+          SinvTask x; x.P = Lb + m.lptr; x.ld = m.ld; x.j0 = j0; x.nb = nb; x.jb = jb; x.inv64 = c->dInv + m.invptr;
+          x.piv = LU ? c->dPiv + m.c0 : nullptr; x.X = c->dSinvF + off; x.XT = LU ? nullptr : c->dSinvB + off;
+          sv.push_back( x );
+          if ( LU ) { SinvTask y = x; y.P = Ub + m.lptr; y.inv64 = c->dInv2 + m.invptr; y.piv = nullptr; y.X = c->dSinvTmp + off; y.XT = c->dSinvB + off; sv.push_back( y ); }
+        }
+      }
+    }
+    if ( c->sinv_tasks.upload( sv ) ) return B200_ERR_CUDA;
+  }
+  /* ---- solve schedule: forward deepest->root, backward root->deepest; one launch per SB-column step of a level */
+  std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<GatherTask> gp;
   std::vector<SLaunch>& SS = c->slaunches;
-  c->max_partial_tiles = 0; c->max_blocks_per_launch = 0;
+  c->max_blocks_per_launch = 0; c->max_part_rows = 0;
   for ( int d = S->maxdepth; d >= 0; d-- ) {
     const std::vector<int>& lv = levels[d];
     if ( c->level_w[d] > 0 ) SS.push_back( { SK_FWD_ZERO_W, d & 1, c->level_w[d], 0, 0, d } );
     { const int64_t g0 = ( int64_t )gp.size();
-      for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } } if ( any ) gp.push_back( s ); }
+      for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
+        if ( any ) for ( int lo = 0; lo < meta[s].f; lo += GATHER_ROWS ) gp.push_back( { s, lo, std::min( meta[s].f, lo + GATHER_ROWS ) } ); }
       if ( ( int64_t )gp.size() > g0 ) SS.push_back( { SK_FWD_GATHER, g0, ( int64_t )gp.size() - g0, 0, 0, d } ); }
+    { const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size(); int64_t prow = 0;
+      for ( int s : lv ) { const SnMeta& m = meta[s]; SolveBlk x; x.sn = s; x.j0 = 0; x.nb = 0; x.la_j0 = 0; x.la_nb = std::min( SB, m.k ); x.la_tiles = ( x.la_nb + FT_ROWS - 1 ) / FT_ROWS; x.la_inv = m.sinv;
+        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
+        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
+        for ( int j = 0; j < x.la_tiles; j++ ) ft.push_back( { id, j * FT_ROWS } ); }
+      c->max_part_rows = std::max( c->max_part_rows, prow );
+      c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
+      SS.push_back( { SK_FWD_FIRST, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } ); }
     int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
-    for ( int j0 = 0; j0 < maxk; j0 += NB ) {
-      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size();
+    for ( int j0 = 0; j0 < maxk; j0 += SB ) {
+      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size(); int64_t prow = 0;
       for ( int s : lv ) {
         const SnMeta& m = meta[s]; if ( j0 >= m.k ) continue;
-        const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
-        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.first_partial = 0; x.ntiles = 0; x.pad = 0;
+        const int nb = std::min( SB, m.k - j0 ); const int below = m.f - j0 - nb;
+        if ( below <= 0 ) continue;
+        const int nbn = std::min( SB, m.k - ( j0 + nb ) );
+        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.la_j0 = j0 + nb; x.la_nb = std::max( nbn, 0 ); x.la_tiles = ( x.la_nb + FT_ROWS - 1 ) / FT_ROWS; x.la_inv = m.sinv + ( int64_t )( j0 / SB + 1 ) * SB * SB;
+        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
         const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
-        ft.push_back( { id, 0 } );                                   /* always one tile: it also stores z */
-        for ( int r0 = 256; r0 < below; r0 += 256 ) ft.push_back( { id, r0 } );
+        for ( int r0 = 0; r0 < below; r0 += FT_ROWS ) ft.push_back( { id, r0 } );
       }
-      SS.push_back( { SK_FWD_BLOCK, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } );
+      if ( ( int64_t )sb.size() == b0 ) continue;
+      c->max_part_rows = std::max( c->max_part_rows, prow );
+      c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
+      SS.push_back( { SK_FWD_STEP, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } );
     }
   }
   for ( int d = 0; d <= S->maxdepth; d++ ) {
     const std::vector<int>& lv = levels[d];
     int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
-    const int nblk = ( maxk + NB - 1 ) / NB;
-    for ( int bi = nblk - 1; bi >= 0; bi-- ) {
-      const int j0 = bi * NB;
-      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )bt.size();
-      int64_t np = 0;
+    const int nblk = ( maxk + SB - 1 ) / SB;
+    /* step nblk: the update rows below the pivots (x gathered from the ancestors); steps nblk-1 .. 1: pivot block t feeds the columns before it */
+    for ( int t = nblk; t >= 1; t-- ) {
+      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )bt.size(); int64_t prow = 0;
       for ( int s : lv ) {
-        const SnMeta& m = meta[s]; if ( j0 >= m.k ) continue;
-        const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
-        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.first_partial = ( int )np; x.ntiles = std::max( 1, ( below + BWD_ROWS - 1 ) / BWD_ROWS ); x.pad = 0;
+        const SnMeta& m = meta[s];
+        const int nbs = ( m.k + SB - 1 ) / SB;
+        SolveBlk x; x.sn = s;
+        int cfirst = 0;
+        if ( t == nblk ) {
+          x.j0 = m.k; x.nb = m.f - m.k; x.la_j0 = ( nbs - 1 ) * SB; x.la_nb = m.k - x.la_j0; x.la_inv = m.sinv + ( int64_t )( nbs - 1 ) * SB * SB;
+          if ( x.nb == 0 ) cfirst = x.la_j0;      /* nothing to subtract: only the tiles that finish the last block */
+        } else {
+          if ( t >= nbs ) continue;
+          x.j0 = t * SB; x.nb = std::min( SB, m.k - x.j0 ); x.la_j0 = x.j0 - SB; x.la_nb = SB; x.la_inv = m.sinv + ( int64_t )( t - 1 ) * SB * SB;
+        }
+        x.la_tiles = ( x.la_nb + BT_COLS - 1 ) / BT_COLS;
+        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
+        const int climit = std::min( x.j0, m.k );
         const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
-        for ( int t = 0; t < x.ntiles; t++ ) bt.push_back( { id, t * BWD_ROWS } );
-        np += x.ntiles;
+        for ( int c0 = cfirst; c0 < climit; c0 += BT_COLS ) bt.push_back( { id, c0 } );
       }
-      c->max_partial_tiles = std::max( c->max_partial_tiles, np );
+      if ( ( int64_t )sb.size() == b0 ) continue;
+      c->max_part_rows = std::max( c->max_part_rows, prow );
       c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
-      SS.push_back( { SK_BWD_BLOCK, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )bt.size() - t0, d } );
+      SS.push_back( { SK_BWD_STEP, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )bt.size() - t0, d } );
     }
   }
-  if ( c->sblk.upload( sb ) || c->fwd_tiles.upload( ft ) || c->bwd_tiles.upload( bt ) || c->gather_parents.upload( gp ) ) return B200_ERR_CUDA;
+  if ( c->sblk.upload( sb ) || c->fwd_tiles.upload( ft ) || c->bwd_tiles.upload( bt ) || c->gather_tasks.upload( gp ) ) return B200_ERR_CUDA;
   c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
                      c->asm_tasks.bytes() + c->sblk.bytes() + c->fwd_tiles.bytes() + c->bwd_tiles.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
   CK( cudaStreamSynchronize( c->stream ) );
@@ -490,6 +540,8 @@ static int run_factor( b200_ctx* c ) {
         fprintf( stderr, "gemm depth=%d tiles=%lld flops=%.3e ms=%.3f TF/s=%.2f\n", l.depth, ( long long )l.count, l.flops, ms, l.flops / ( ms * 1e-3 ) / 1e12 );
     }
   }
+  /* explicit inverses of the solve blocks (feeds the sweeps; part of the factorization time) */
+  if ( c->sinv_tasks.n ) { build_sinv_kernel<<<( unsigned )c->sinv_tasks.n, 256, SINV_SMEM, st>>>( c->sinv_tasks.d ); nlaunch++; }
   CK( cudaEventRecord( c->ev1, st ) );
   CK( cudaGetLastError() );
   int err = 0, pert = 0;
@@ -533,13 +585,13 @@ extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
 /* -------------------------------------------------------------- solve */
 static int ensure_solve_ws( b200_ctx* c, int p ) {
   if ( p <= c->solve_p_cap ) return B200_OK;
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dPartial ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets );
-  c->dY = c->dW[0] = c->dW[1] = c->dPartial = c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->solve_p_cap = 0;
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart ); c->dPart = nullptr;
+  c->dY = c->dW[0] = c->dW[1] = c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->solve_p_cap = 0;
   CK( cudaMalloc( &c->dY, ( size_t )c->n * p * 8 ) );
   CK( cudaMalloc( &c->dR, ( size_t )c->n * p * 8 ) ); CK( cudaMalloc( &c->dD, ( size_t )c->n * p * 8 ) );
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dW[a], ( size_t )std::max<int64_t>( c->w_rows[a], 1 ) * p * 8 ) );
-  const int pchunks = ( p + PC - 1 ) / PC;
-  CK( cudaMalloc( &c->dPartial, ( size_t )std::max<int64_t>( c->max_partial_tiles, 1 ) * pchunks * NB * PC * 8 ) );
+  const int pchunks = p;     /* upper bound for either chunking (1 or 8 right-hand sides per CTA) */
+  CK( cudaMalloc( &c->dPart, ( size_t )std::max<int64_t>( c->max_part_rows, 1 ) * p * 8 ) );
   CK( cudaMalloc( &c->dZ, ( size_t )c->n * p * 8 ) );
   { const size_t tb = ( size_t )std::max<int64_t>( c->max_blocks_per_launch, 1 ) * pchunks * sizeof( unsigned int ); CK( cudaMalloc( &c->dTickets, tb ) ); CK( cudaMemsetAsync( c->dTickets, 0, tb, c->stream ) ); }
   c->solve_p_cap = p;
@@ -551,11 +603,14 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
   const bool LU = c->kind == B200_KIND_LU;
   cudaStream_t st = c->stream;
   const int n = c->n;
-  const int pchunks = ( p + PC - 1 ) / PC;
+  const int gchunks = ( p + PC - 1 ) / PC;                 /* gather: 8 right-hand sides per CTA */
+  const bool one = p == 1;                                 /* sweep kernels: 1 or 8 right-hand sides per CTA */
+  const int pchunks = one ? 1 : ( p + 7 ) / 8;
   const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * p + 255 ) / 256, 148 * 32 );
   permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, c->dY );
   nl += 2;
   const int64_t ldw[2] = { std::max<int64_t>( c->w_rows[0], 1 ), std::max<int64_t>( c->w_rows[1], 1 ) };
+  const double* Mb = LU ? c->dU : c->dL;
   for ( const SLaunch& l : c->slaunches ) {
     const int a = l.depth & 1, ac = ( l.depth + 1 ) & 1;
     if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
@@ -564,13 +619,20 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
         CK( cudaMemset2DAsync( c->dW[a], ( size_t )ldw[a] * 8, 0, ( size_t )l.count * 8, ( size_t )p, st ) );
         break;
       case SK_FWD_GATHER:
-        fwd_gather_kernel<<<dim3( ( unsigned )l.count, pchunks ), 256, 0, st>>>( c->gather_parents.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, n, p, c->dW[a], ldw[a], c->dW[ac], ldw[ac] );
+        fwd_gather_kernel<<<dim3( ( unsigned )l.count, gchunks ), 256, 0, st>>>( c->gather_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, n, p, c->dW[a], ldw[a], c->dW[ac], ldw[ac] );
         break;
-      case SK_FWD_BLOCK:
-        fwd_block_kernel<<<dim3( ( unsigned )l.ntiles, pchunks ), 256, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dInv, LU ? c->dPiv : nullptr, c->dY, c->dZ, n, p, c->dW[a], ldw[a] );
+      case SK_FWD_FIRST:
+        if ( one ) solve_first_block_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dSinvF, c->dY, c->dZ, n, p, c->dPart, c->dTickets );
+        else solve_first_block_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dSinvF, c->dY, c->dZ, n, p, c->dPart, c->dTickets );
         break;
-      case SK_BWD_BLOCK:
-        bwd_block_kernel<<<dim3( ( unsigned )l.ntiles, pchunks ), 256, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, LU ? c->dU : c->dL, LU ? c->dInv2 : c->dInv, c->rowidx.d, c->dZ, n, p, c->dPartial, c->dTickets );
+      case SK_FWD_STEP:
+        if ( one ) solve_fwd_step_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, n, p, c->dW[a], ldw[a], c->dPart, c->dTickets );
+        else solve_fwd_step_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, n, p, c->dW[a], ldw[a], c->dPart, c->dTickets );
+        break;
+      case SK_BWD_STEP:
+        if ( l.ntiles == 0 ) break;
+        if ( one ) solve_bwd_step_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dZ, n, p, c->dPart, c->dTickets );
+        else solve_bwd_step_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dZ, n, p, c->dPart, c->dTickets );
         break;
     }
     nl++;
@@ -597,7 +659,7 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
    * known-answer tolerances ask for); otherwise only while the componentwise backward error
    * max_i |r_i| / (|A||x|+|b|)_i exceeds 1e-15. */
   const int maxit = c->refine >= 0 ? c->refine : 2;
-  c->stats.refine_steps = 0; c->stats.backward_error = -1.0;
+  c->stats.refine_steps = 0; c->stats.backward_error = -1.0; c->stats.first_backward_error = -1.0;
   for ( int it = 0; it < maxit; it++ ) {
     CK( cudaMemsetAsync( c->dOmega, 0, sizeof( unsigned long long ), st ) );
     residual_dd_kernel<<<pblocks, 256, 0, st>>>( c->spmv_ptr.d, c->spmv_col.d, c->spmv_src.d, c->dVals, d_x, d_b, n, p, c->dR, c->dOmega );
@@ -607,7 +669,7 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
       CK( cudaMemcpyAsync( &bits, c->dOmega, sizeof( bits ), cudaMemcpyDeviceToHost, st ) );
       CK( cudaStreamSynchronize( st ) );
       double omega; memcpy( &omega, &bits, sizeof( omega ) );
-      c->stats.backward_error = omega;
+      c->stats.backward_error = omega; if ( it == 0 ) c->stats.first_backward_error = omega;
       const bool small = n <= 65536;     /* depends on n only: the answer must not depend on how columns are batched */
       if ( !( ( small && it == 0 ) || omega > 1e-15 ) ) break;
     }
@@ -679,7 +741,7 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   std::string s;
   char line[256];
   for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
-  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_block", "solve_bwd_block" };
+  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_first", "solve_fwd_step", "solve_bwd_step" };
   for ( int k = 0; k < SK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", sname[k], ( long long )c->sprof_n[k], c->sprof_ms[k] ); s += line; }
   snprintf( buf, len, "%s", s.c_str() );
   return B200_OK;
@@ -689,7 +751,7 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
 extern "C" int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count ) {
   if ( !c || !dst ) return B200_ERR_ARG;
   CK( cudaSetDevice( c->device ) );
-  const double* src = which == 0 ? c->dL : which == 1 ? c->dU : c->dInv;
+  const double* src = which == 0 ? c->dL : which == 1 ? c->dU : which == 2 ? c->dInv : which == 3 ? c->dSinvF : c->dSinvB;
   if ( !src ) return B200_ERR_STATE;
   CK( cudaMemcpy( dst, src + offset, ( size_t )count * 8, cudaMemcpyDeviceToHost ) );
   return B200_OK;
