@@ -142,6 +142,39 @@ void b200_host_free_pinned( void* p );
 int b200_dev_sync( b200_ctx_t* c );
 int b200_flush_l2( b200_ctx_t* c );             /* write a >L2 buffer between timed steps */
 
+
+/* ---- one factorization on several GPUs (csrc/host/b200_plan.c; Cholesky only in this round)
+ * Every rank runs the same analysis and derives the same plan; rank r then executes only the
+ * work it owns.  Supernode s belongs to the contiguous rank group [grp_first[s], +grp_size[s])
+ * (proportional mapping of subtree flops); if dist[s] its front columns are dealt out in blocks
+ * of level_width[depth] columns, block b to rank grp_first + b mod grp_size, otherwise rank
+ * grp_first owns all of it. */
+typedef struct b200_plan {
+  int world, ns, nlevels;
+  int* grp_first;      /* [ns] */
+  int* grp_size;       /* [ns] */
+  int* dist;           /* [ns] 1: front distributed column-block-cyclically over its group */
+  double* work;        /* [ns] flops of the subtree rooted at s (relaxed structure)        */
+  int* level_width;    /* [nlevels] outer panel width = column block width of the level    */
+} b200_plan_t;
+typedef struct b200_xfer { int src, dst, sn; int64_t offset, count; } b200_xfer_t;   /* doubles, inside the child's contribution-block arena */
+
+int b200_outer_width( int maxfront );
+b200_plan_t* b200_plan_create( const b200_symbolic_t* S, int world, int min_dist_front );
+void b200_plan_free( b200_plan_t* pl );
+int b200_plan_col_owner( const b200_plan_t* pl, const b200_symbolic_t* S, int s, int c );
+int b200_plan_member( const b200_plan_t* pl, int s, int r );
+int64_t b200_plan_cb_transfers( const b200_plan_t* pl, const b200_symbolic_t* S, int depth, b200_xfer_t* out, int64_t cap );
+
+/* multi-process mode (one process per GPU, e.g. under torchrun): rank 0 creates a 128-byte NCCL id,
+ * the launcher hands it to every rank (bench.py: torch.distributed broadcast), and each rank joins
+ * BEFORE b200_upload_symbolic.  Panels of distributed fronts and contribution-block columns at subtree
+ * boundaries then move with NCCL over NVLink inside b200_factor_*; afterwards every rank holds the
+ * whole factor and b200_solve_* works on any of them. */
+int b200_mg_unique_id( char* out128 );
+int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id128 );
+int b200_mg_rank( b200_ctx_t* c, int* rank, int* world );
+
 /* iterative refinement: r = b - A x is accumulated in double-double on the device, then one more
  * pair of sweeps corrects x.  steps >= 0: exactly that many; steps < 0 (default): automatic -- one
  * step for small systems (n <= 65536), otherwise only while the componentwise backward error

@@ -63,6 +63,15 @@ class b200_stats_t(C.Structure):
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("device_bytes", C.c_int64), ("npiv_perturbed", C.c_int), ("refine_steps", C.c_int), ("backward_error", C.c_double), ("first_backward_error", C.c_double)]
 
 
+class b200_plan_t(C.Structure):
+    _fields_ = [("world", C.c_int), ("ns", C.c_int), ("nlevels", C.c_int), ("grp_first", C.POINTER(C.c_int)), ("grp_size", C.POINTER(C.c_int)),
+                ("dist", C.POINTER(C.c_int)), ("work", C.POINTER(C.c_double)), ("level_width", C.POINTER(C.c_int))]
+
+
+class b200_xfer_t(C.Structure):
+    _fields_ = [("src", C.c_int), ("dst", C.c_int), ("sn", C.c_int), ("offset", C.c_int64), ("count", C.c_int64)]
+
+
 # every symbol include/*.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     # mc_matrix.h
@@ -81,6 +90,8 @@ EXPORTED_SYMBOLS = [
     "b200_solve_host", "b200_solve_device", "b200_dev_alloc", "b200_dev_free", "b200_dev_upload", "b200_dev_download",
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
     "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dgemm_variant", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
+    "b200_outer_width", "b200_plan_create", "b200_plan_free", "b200_plan_col_owner", "b200_plan_member", "b200_plan_cb_transfers",
+    "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank",
 ]
 
 _lib = None
@@ -134,6 +145,14 @@ def lib():
     L.b200_symbolic_free.argtypes = [C.POINTER(b200_symbolic_t)]
     L.b200_order_nd.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), i32, i32, C.POINTER(i32)]
     L.b200_etree.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.b200_plan_create.restype = C.POINTER(b200_plan_t); L.b200_plan_create.argtypes = [C.POINTER(b200_symbolic_t), i32, i32]
+    L.b200_plan_free.argtypes = [C.POINTER(b200_plan_t)]
+    L.b200_plan_col_owner.argtypes = [C.POINTER(b200_plan_t), C.POINTER(b200_symbolic_t), i32, i32]
+    L.b200_plan_member.argtypes = [C.POINTER(b200_plan_t), i32, i32]
+    L.b200_plan_cb_transfers.restype = i64; L.b200_plan_cb_transfers.argtypes = [C.POINTER(b200_plan_t), C.POINTER(b200_symbolic_t), i32, C.POINTER(b200_xfer_t), i64]
+    L.b200_mg_unique_id.argtypes = [C.c_char_p]
+    L.b200_mg_init.argtypes = [vp, i32, i32, C.c_char_p]
+    L.b200_mg_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.b200_ctx_create.restype = vp; L.b200_ctx_create.argtypes = [i32]
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_last_error.restype = C.c_char_p
@@ -257,6 +276,22 @@ class Solver:
 
     def err(self):
         return self.L.b200_last_error().decode()
+
+    def join(self, rank, world, id128=None, dist=None):
+        """multi-process mode: one rank per GPU.  Either pass the 128-byte NCCL id, or a torch.distributed
+        module with an initialised process group (rank 0 creates the id and broadcasts it)."""
+        if world > 1 and id128 is None:
+            import torch
+            buf = C.create_string_buffer(128)
+            if rank == 0 and self.L.b200_mg_unique_id(buf) != B200_OK:
+                raise RuntimeError("b200_mg_unique_id: " + self.err())
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0)
+            id128 = bytes(t.cpu().tolist())
+        r = self.L.b200_mg_init(self.ctx, rank, world, id128)
+        if r != B200_OK:
+            raise RuntimeError("b200_mg_init: " + self.err())
 
     def analyze(self, n, colptr, rowidx, kind=KIND_CHOLESKY, **kw):
         if self.S:

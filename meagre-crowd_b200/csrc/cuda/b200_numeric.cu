@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <dlfcn.h>
+#include <nccl.h>      /* types only: the library is bound at run time (the copy torch has already loaded, else the system one) */
 #include "solver_b200.h"
 #include "b200_kernels.cuh"
 
@@ -34,8 +36,41 @@ extern "C" const char* b200_last_error( void ) { return g_err; }
 #define CK( call ) do { cudaError_t e_ = ( call ); if ( e_ != cudaSuccess ) { set_err( "%s: %s", #call, cudaGetErrorString( e_ ) ); return B200_ERR_CUDA; } } while ( 0 )
 #define CKN( call ) do { cudaError_t e_ = ( call ); if ( e_ != cudaSuccess ) { set_err( "%s: %s", #call, cudaGetErrorString( e_ ) ); return nullptr; } } while ( 0 )
 
+
+/* ------------------------------------------------------------ NCCL binding
+ * Resolved with dlopen/dlsym so that libmeagre_crowd_b200.so has no link-time dependency on NCCL:
+ * a single-GPU user never loads it, and under torchrun the soname resolves to the copy torch
+ * brought in (one NCCL per process). */
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t ( *GetUniqueId )( ncclUniqueId* ) = nullptr;
+  ncclResult_t ( *CommInitRank )( ncclComm_t*, int, ncclUniqueId, int ) = nullptr;
+  ncclResult_t ( *CommDestroy )( ncclComm_t ) = nullptr;
+  ncclResult_t ( *Send )( const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t ) = nullptr;
+  ncclResult_t ( *Recv )( void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t ) = nullptr;
+  ncclResult_t ( *GroupStart )() = nullptr;
+  ncclResult_t ( *GroupEnd )() = nullptr;
+  const char* ( *GetErrorString )( ncclResult_t ) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if ( g_nccl.h ) return 0;
+  const char* names[] = { "libnccl.so.2", "libnccl.so" };
+  void* h = nullptr;
+  for ( const char* nm : names ) { h = dlopen( nm, RTLD_NOW | RTLD_GLOBAL ); if ( h ) break; }
+  if ( !h ) { set_err( "cannot load NCCL: %s", dlerror() ); return -1; }
+#define B200_SYM( field, name ) g_nccl.field = reinterpret_cast<decltype( g_nccl.field )>( dlsym( h, name ) ); if ( !g_nccl.field ) { set_err( "NCCL lacks %s", name ); return -1; }
+  B200_SYM( GetUniqueId, "ncclGetUniqueId" ) B200_SYM( CommInitRank, "ncclCommInitRank" ) B200_SYM( CommDestroy, "ncclCommDestroy" )
+  B200_SYM( Send, "ncclSend" ) B200_SYM( Recv, "ncclRecv" ) B200_SYM( GroupStart, "ncclGroupStart" ) B200_SYM( GroupEnd, "ncclGroupEnd" )
+  B200_SYM( GetErrorString, "ncclGetErrorString" )
+#undef B200_SYM
+  g_nccl.h = h;
+  return 0;
+}
+#define NK( call ) do { ncclResult_t r_ = ( call ); if ( r_ != ncclSuccess ) { set_err( "%s: %s", #call, g_nccl.GetErrorString( r_ ) ); return B200_ERR_CUDA; } } while ( 0 )
+
 /* outer panel width = K of the trailing update; chosen per tree level from its largest front */
-static inline int outer_width( int maxfront ) { return maxfront >= 6144 ? 512 : maxfront >= 1536 ? 256 : 128; }
+static inline int outer_width( int maxfront ) { return b200_outer_width( maxfront ); }
 constexpr int ASM_COLS = 32;  /* destination columns per extend-add CTA */
 constexpr int GEMM_STAGES = 4;
 /* production tile of the DMMA update kernel: 64x64 per CTA, 8 warps of 32x16, 4-stage cp.async pipeline.
@@ -47,10 +82,12 @@ constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 
-enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_NOP, LK_COUNT };
-static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused", "nop" };
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_NOP, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused", "nop", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
+/* one point-to-point message of the multi-GPU schedule: which = 0 L storage, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
+struct Msg { int src, dst, which; int64_t off, cnt; };
 
-/* stream 0 = update stream (also level prologues), stream 1 = panel stream (look-ahead);
+/* stream 0 = update stream (also level prologues), stream 1 = panel stream (look-ahead), stream 2 = NCCL stream;
  * wait_ev / record_ev index ctx->events (-1: none) */
 struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; int stream = 0; int wait_ev = -1; int record_ev = -1; };
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
@@ -74,7 +111,8 @@ template <class T> struct DevVec {
 
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+  int rank = 0, world = 1; ncclComm_t comm = nullptr; b200_plan_t* plan = nullptr; std::vector<Msg> msgs; double comm_bytes = 0;
   std::vector<cudaEvent_t> events; int nevents = 0;
   cudaDeviceProp prop;
   /* symbolic copy */
@@ -114,7 +152,7 @@ struct b200_ctx {
   double sprof_ms[SK_COUNT] = { 0 }; int64_t sprof_n[SK_COUNT] = { 0 };
   double tiny = 0.0;
   b200_stats_t stats;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evs = nullptr;
   int64_t device_bytes = 0;
 };
 
@@ -129,8 +167,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->device = device;
   CKN( cudaGetDeviceProperties( &c->prop, device ) );
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
-    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); }
-  CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) );
+    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); }
+  CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
@@ -144,6 +182,31 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   return c;
 }
 
+
+/* ------------------------------------------------------------ multi-process mode */
+extern "C" int b200_mg_unique_id( char* out128 ) {
+  if ( !out128 ) return B200_ERR_ARG;
+  if ( load_nccl() ) return B200_ERR_CUDA;
+  ncclUniqueId id; static_assert( sizeof( ncclUniqueId ) == 128, "NCCL id is 128 bytes" );
+  NK( g_nccl.GetUniqueId( &id ) );
+  memcpy( out128, &id, 128 );
+  return B200_OK;
+}
+extern "C" int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id128 ) {
+  if ( !c || world < 1 || rank < 0 || rank >= world ) return B200_ERR_ARG;
+  if ( c->dL ) { set_err( "b200_mg_init must precede b200_upload_symbolic%s", "" ); return B200_ERR_STATE; }
+  CK( cudaSetDevice( c->device ) );
+  if ( c->comm ) { g_nccl.CommDestroy( c->comm ); c->comm = nullptr; }
+  c->rank = rank; c->world = world;
+  if ( world == 1 ) return B200_OK;
+  if ( !id128 ) return B200_ERR_ARG;
+  if ( load_nccl() ) return B200_ERR_CUDA;
+  ncclUniqueId id; memcpy( &id, id128, 128 );
+  NK( g_nccl.CommInitRank( &c->comm, world, id, rank ) );
+  return B200_OK;
+}
+extern "C" int b200_mg_rank( b200_ctx_t* c, int* rank, int* world ) { if ( !c ) return B200_ERR_ARG; if ( rank ) *rank = c->rank; if ( world ) *world = c->world; return B200_OK; }
+
 static void release_symbolic( b200_ctx* c ) {
   cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
   cudaFree( c->dSinvF ); cudaFree( c->dSinvB ); cudaFree( c->dSinvTmp ); c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr; c->sinv_tasks.release();
@@ -154,7 +217,7 @@ static void release_symbolic( b200_ctx* c ) {
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart );
   c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->dPart = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
-  c->launches.clear(); c->slaunches.clear(); c->nevents = 0;
+  c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
   c->factored = false; c->device_bytes = 0;
 }
 
@@ -164,9 +227,11 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   cudaStreamSynchronize( c->stream );
   release_symbolic( c );
   cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
-  cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 );
+  cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
-  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 );
+  if ( c->comm ) g_nccl.CommDestroy( c->comm );
+  if ( c->plan ) b200_plan_free( c->plan );
+  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 ); cudaStreamDestroy( c->stream3 );
   delete c;
 }
 
@@ -227,6 +292,13 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     m.wptr = c->level_w[d]; c->level_w[d] += u;
   }
   c->invsize = invoff; c->sinvsize = sinvoff;
+  if ( c->world > 1 ) {
+    if ( LU ) { set_err( "multi-GPU factorization is built for Cholesky only (LU: run on one GPU)%s", "" ); return B200_ERR_ARG; }
+    const char* md = getenv( "B200_MIN_DIST_FRONT" );
+    c->plan = b200_plan_create( S, c->world, md ? atoi( md ) : 2048 );
+    if ( !c->plan ) return B200_ERR_NOMEM;
+  }
+  c->comm_bytes = 0;
   c->w_rows[0] = c->w_rows[1] = 0;
   for ( int d = 0; d <= S->maxdepth; d++ ) c->w_rows[d & 1] = std::max( c->w_rows[d & 1], c->level_w[d] );
 
@@ -253,35 +325,62 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( c->child_list.upload( child_list ) ) return B200_ERR_CUDA;
   if ( c->sn.upload( meta ) ) return B200_ERR_CUDA;
 
-  /* ---- factor schedule */
+  /* ---- factor schedule.  With more than one rank (b200_mg_init) every rank walks the same loops and keeps
+   * only the work it owns (b200_plan.c); messages are emitted in the same global order on every rank. */
   g_alg_flops = 0;
   std::vector<GemmTask> gt; std::vector<Tile> tb, ts; std::vector<DiagTask> dt; std::vector<TrsmTask> tt; std::vector<RowTile> ttl; std::vector<AsmTask> at;
   std::vector<Launch>& LS = c->launches;
+  std::vector<Msg>& MS = c->msgs;
   double* Lb = c->dL; double* Ub = c->dU;
+  const bool MG = c->world > 1;
+  const int me = c->rank;
+  const b200_plan_t* pl = c->plan;
+  auto is_dist = [&]( int s ) { return MG && pl->dist[s] != 0; };
+  auto member = [&]( int s ) { return !MG || b200_plan_member( pl, s, me ) != 0; };
+  auto owns = [&]( int s, int col ) { return !MG || b200_plan_col_owner( pl, S, s, col ) == me; };
+  auto new_event = [&]() { return c->nevents++; };
+  /* join helpers: make stream `to` wait for everything issued so far on stream `from` */
+  auto push_nop = [&]( int d, int stream ) { Launch l = { LK_NOP, 0, 0, d, 0.0 }; l.stream = stream; LS.push_back( l ); };
   for ( int d = S->maxdepth; d >= 0; d-- ) {
-    const std::vector<int>& lv = levels[d];
+    std::vector<int> lv;                                     /* the supernodes of this level I take part in */
+    int maxf_all = 0;
+    for ( int s : levels[d] ) { maxf_all = std::max( maxf_all, meta[s].f ); if ( member( s ) ) lv.push_back( s ); }
     double* CB = c->dCB[d & 1];
     if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, d & 1, c->level_cb[d], d, 0.0 } );
-    { /* extend-add of the children (they live at depth d+1) */
+    if ( MG ) { /* contribution-block columns computed elsewhere that my part of this level's fronts needs, and vice versa */
+      const int64_t nx = b200_plan_cb_transfers( pl, S, d, nullptr, 0 );
+      if ( nx > 0 ) {
+        std::vector<b200_xfer_t> xs( nx ); b200_plan_cb_transfers( pl, S, d, xs.data(), nx );
+        const int64_t m0 = ( int64_t )MS.size();
+        for ( const b200_xfer_t& x : xs ) if ( x.src == me || x.dst == me ) { MS.push_back( { x.src, x.dst, 2 + ( ( d + 1 ) & 1 ), x.offset, x.count } ); c->comm_bytes += ( double )x.count * 8.0; }
+        if ( ( int64_t )MS.size() > m0 ) {
+          const int ea = new_event(), eb = new_event();
+          push_nop( d, 0 ); LS.back().record_ev = ea;
+          Launch l = { LK_XFER_CB, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = ea; l.record_ev = eb; LS.push_back( l );
+          push_nop( d, 0 ); LS.back().wait_ev = eb;
+        }
+      }
+    }
+    { /* extend-add of the children (they live at depth d+1) into the destination columns I own */
       const int64_t first = ( int64_t )at.size();
       for ( int s : lv ) {
         if ( meta[s].child_begin == meta[s].child_end ) continue;
         bool any = false;
         for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
         if ( !any ) continue;
-        for ( int c0 = 0; c0 < meta[s].f; c0 += ASM_COLS ) at.push_back( { s, c0, std::min( ASM_COLS, meta[s].f - c0 ) } );
+        for ( int c0 = 0; c0 < meta[s].f; c0 += ASM_COLS ) if ( owns( s, c0 ) ) at.push_back( { s, c0, std::min( ASM_COLS, meta[s].f - c0 ) } );
       }
       if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
     }
-    int maxk = 0, maxf = 0;
-    for ( int s : lv ) { maxk = std::max( maxk, meta[s].k ); maxf = std::max( maxf, meta[s].f ); }
-    const int NBO = outer_width( maxf );
+    int maxk = 0; bool any_dist = false;
+    for ( int s : lv ) { maxk = std::max( maxk, meta[s].k ); any_dist = any_dist || is_dist( s ); }
+    const int NBO = outer_width( maxf_all );
     /* look-ahead: with more than one outer panel, the next panel is factored on a second stream while
      * the bulk of the trailing update of the current one still runs on the first */
-    const bool look = maxk > NBO;
+    const bool look = maxk > NBO || any_dist;
     int ev_next = -1;                       /* recorded after update_next(J-1): panel(J) may start */
     if ( look ) {                           /* level prologue (and everything before it) done */
-      if ( LS.empty() || LS.back().record_ev >= 0 || LS.back().stream != 0 ) LS.push_back( { LK_NOP, 0, 0, d, 0.0 } );
+      if ( LS.empty() || LS.back().record_ev >= 0 || LS.back().stream != 0 ) push_nop( d, 0 );
       LS.back().record_ev = c->nevents; ev_next = c->nevents++;
     }
     for ( int J = 0; J < maxk; J += NBO ) {
@@ -290,7 +389,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         const int64_t d0 = ( int64_t )dt.size();
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
-          if ( j0 >= m.k ) continue;
+          if ( j0 >= m.k || !owns( s, J ) ) continue;
           const int nb = std::min( NB, m.k - j0 );
           DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
           x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
@@ -301,11 +400,11 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( ( int64_t )dt.size() == d0 ) break;
         LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
         /* rows below the diagonal block */
-        const int64_t t0 = ( int64_t )tt.size(), tl0 = ( int64_t )ttl.size();
+        const int64_t tl0 = ( int64_t )ttl.size();
         double tflops = 0;
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
-          if ( j0 >= m.k ) continue;
+          if ( j0 >= m.k || !owns( s, J ) ) continue;
           const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
           if ( below <= 0 ) continue;
           const double* inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB;
@@ -322,13 +421,12 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           }
         }
         if ( ( int64_t )ttl.size() > tl0 ) LS.push_back( { LK_TRSM, tl0, ( int64_t )ttl.size() - tl0, d, tflops } );
-        ( void )t0;
         /* update of the remaining columns of this outer panel */
-        const int64_t b0 = ( int64_t )tb.size(), s0 = ( int64_t )ts.size();
-        double fb = 0, fs = 0;
+        const int64_t b0 = ( int64_t )tb.size();
+        double fb = 0;
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
-          if ( j0 >= m.k ) continue;
+          if ( j0 >= m.k || !owns( s, J ) ) continue;
           const int nb = std::min( NB, m.k - j0 ); const int jn = j0 + nb; const int jend = std::min( m.k, J + NBO );
           if ( jn >= jend ) continue;
           double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
@@ -340,16 +438,31 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           }
           fb += fl;
         }
-        ( void )fs;
-        if ( ( int64_t )tb.size() > b0 ) LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } );
-        if ( ( int64_t )ts.size() > s0 ) LS.push_back( { LK_GEMM_SMALL, s0, ( int64_t )ts.size() - s0, d, 0.0 } );
-        if ( !LS.empty() && ( LS.back().kind == LK_GEMM_BIG || LS.back().kind == LK_GEMM_SMALL ) ) LS.back().flops += fb;
+        if ( ( int64_t )tb.size() > b0 ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } ); LS.back().flops += fb; }
       }
       int ev_panel = -1;
       if ( look && LS.size() > panel_first ) {
         for ( size_t q = panel_first; q < LS.size(); q++ ) LS[q].stream = 1;
         LS[panel_first].wait_ev = ev_next;
         LS.back().record_ev = c->nevents; ev_panel = c->nevents++;
+      }
+      if ( any_dist ) { /* the factored panels (and their diagonal-block inverses) go from their owner to the rest of the group */
+        const int64_t m0 = ( int64_t )MS.size();
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( !is_dist( s ) || J >= m.k ) continue;
+          const int root = b200_plan_col_owner( pl, S, s, J ); const int kb = std::min( NBO, m.k - J );
+          for ( int r = pl->grp_first[s]; r < pl->grp_first[s] + pl->grp_size[s]; r++ ) {
+            if ( r == root || ( me != root && me != r ) ) continue;
+            MS.push_back( { root, r, 0, m.lptr + ( int64_t )J * m.ld, ( int64_t )kb * m.ld } );
+            MS.push_back( { root, r, 1, m.invptr + ( int64_t )( J / NB ) * NB * NB, ( int64_t )( kb / NB ) * NB * NB + ( int64_t )( kb % NB ) * ( kb % NB ) } );
+            c->comm_bytes += ( double )kb * m.ld * 8.0;
+          }
+        }
+        if ( ( int64_t )MS.size() > m0 ) {
+          Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = ev_panel; l.record_ev = c->nevents; ev_panel = c->nevents++;
+          LS.push_back( l );
+        }
       }
       /* trailing update with the whole outer panel, in two launches: first the columns of the NEXT
        * outer panel (all the next panel factorization depends on), then the remaining pivot columns
@@ -364,6 +477,23 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           const int Jn2 = std::min( m.k, Jn + NBO );           /* end of the next outer panel */
           double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
           double* cb = CB + m.cbptr;
+          if ( is_dist( s ) ) { /* my column blocks only (Cholesky) */
+            const int ldu = ( u + 1 ) & ~1;
+            if ( part == 0 ) {
+              if ( Jn < Jn2 && owns( s, Jn ) ) { double* Cl = Lp + Jn + ( int64_t )Jn * m.ld; const double* Al = Lp + Jn + ( int64_t )J * m.ld; add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Al, m.ld, m.f - Jn, Jn2 - Jn, kb, 1, 0 ); }
+            } else {
+              for ( int blk = Jn2 / NBO; blk * NBO < m.f; blk++ ) {
+                if ( !owns( s, blk * NBO ) ) continue;
+                const int c_lo = std::max( blk * NBO, Jn2 ), c_hi = std::min( ( blk + 1 ) * NBO, m.f );
+                if ( c_lo >= c_hi ) continue;
+                const int p_hi = std::min( c_hi, m.k );
+                if ( c_lo < p_hi ) { double* Cl = Lp + c_lo + ( int64_t )c_lo * m.ld; const double* Al = Lp + c_lo + ( int64_t )J * m.ld; add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Al, m.ld, m.f - c_lo, p_hi - c_lo, kb, 1, 0 ); }
+                const int j_lo = std::max( c_lo, m.k ) - m.k, j_hi = c_hi - m.k;
+                if ( j_lo < j_hi ) { const double* Al = Lp + ( m.k + j_lo ) + ( int64_t )J * m.ld; add_gemm( gt, tb, ts, fl, cb + j_lo + ( int64_t )j_lo * ldu, ldu, Al, m.ld, Al, m.ld, u - j_lo, j_hi - j_lo, kb, 1, 0 ); }
+              }
+            }
+            continue;
+          }
           const int c_lo = part == 0 ? Jn : Jn2, c_hi = part == 0 ? Jn2 : m.k;   /* pivot columns updated by this part */
           if ( c_lo < c_hi ) {
             double* Cl = Lp + c_lo + ( int64_t )c_lo * m.ld; const double* Al = Lp + c_lo + ( int64_t )J * m.ld;
@@ -384,14 +514,40 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( any ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, fl } ); }
         if ( look ) {
           if ( part == 0 ) {
-            if ( !any ) LS.push_back( { LK_NOP, 0, 0, d, 0.0 } );
+            if ( !any ) push_nop( d, 0 );
             LS.back().wait_ev = ev_panel;                               /* update stream waits for the panel */
             LS.back().record_ev = c->nevents; ev_next = c->nevents++;   /* next panel may start */
           }
         }
       }
     }
-    if ( look ) { /* the level's last panel event is already waited on by its update; nothing left on stream 1 */ }
+  }
+  if ( MG ) { /* every rank ends up with the whole factor (L panels and diagonal-block inverses): holders send what the others lack */
+    const int64_t m0 = ( int64_t )MS.size();
+    auto emit = [&]( int s0, int s1, int h0, int hn ) {     /* supernodes s0..s1 held by ranks [h0, h0+hn) */
+      const int64_t lo = meta[s0].lptr, lcnt = S->lptr[s1 + 1] - lo;
+      const int64_t io = meta[s0].invptr, icnt = ( s1 + 1 < ns ? meta[s1 + 1].invptr : c->invsize ) - io;
+      for ( int r = 0; r < c->world; r++ ) {
+        if ( r >= h0 && r < h0 + hn ) continue;
+        if ( me != h0 && me != r ) continue;
+        if ( lcnt > 0 ) { MS.push_back( { h0, r, 0, lo, lcnt } ); c->comm_bytes += ( double )lcnt * 8.0; }
+        if ( icnt > 0 ) MS.push_back( { h0, r, 1, io, icnt } );
+      }
+    };
+    int s0 = 0;
+    while ( s0 < ns ) {
+      if ( pl->dist[s0] ) { emit( s0, s0, pl->grp_first[s0], pl->grp_size[s0] ); s0++; continue; }
+      int s1 = s0;
+      while ( s1 + 1 < ns && !pl->dist[s1 + 1] && pl->grp_first[s1 + 1] == pl->grp_first[s0] ) s1++;
+      emit( s0, s1, pl->grp_first[s0], 1 );
+      s0 = s1 + 1;
+    }
+    if ( ( int64_t )MS.size() > m0 ) {
+      const int ea = new_event(), eb = new_event();
+      push_nop( 0, 0 ); LS.back().record_ev = ea;
+      Launch l = { LK_GATHER, m0, ( int64_t )MS.size() - m0, 0, 0.0 }; l.stream = 2; l.wait_ev = ea; l.record_ev = eb; LS.push_back( l );
+      push_nop( 0, 0 ); LS.back().wait_ev = eb;
+    }
   }
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
@@ -505,11 +661,12 @@ static int run_factor( b200_ctx* c ) {
     const int blocks = ( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 16 );
     scatter_A_kernel<<<blocks, 256, 0, st>>>( c->dVals, c->amap.d, c->nnzA, c->dL, c->dU );
   }
+  if ( c->world > 1 ) { CK( cudaEventRecord( c->evs, st ) ); CK( cudaStreamWaitEvent( c->stream3, c->evs, 0 ) ); }   /* nothing may land in L before it has been zeroed and scattered */
   int64_t nlaunch = 3 + ( LU ? 1 : 0 );
   double gemm_flops = 0; int64_t gemm_launches = 0;
   for ( int k = 0; k < LK_COUNT; k++ ) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
   for ( const Launch& l : c->launches ) {
-    cudaStream_t ls = l.stream ? c->stream2 : c->stream;
+    cudaStream_t ls = l.stream == 0 ? c->stream : l.stream == 1 ? c->stream2 : c->stream3;
     if ( l.wait_ev >= 0 ) CK( cudaStreamWaitEvent( ls, c->events[l.wait_ev], 0 ) );
     if ( c->profile ) CK( cudaEventRecord( c->evp0, ls ) );
     switch ( l.kind ) {
@@ -529,6 +686,16 @@ static int run_factor( b200_ctx* c ) {
         else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
         gemm_flops += l.flops; gemm_launches++; break;
       case LK_NOP: break;
+      case LK_XFER_CB: case LK_BCAST: case LK_GATHER: {
+        NK( g_nccl.GroupStart() );
+        for ( int64_t i = l.first; i < l.first + l.count; i++ ) {
+          const Msg& m = c->msgs[i];
+          double* base = m.which == 0 ? c->dL : m.which == 1 ? c->dInv : c->dCB[m.which - 2];
+          if ( m.src == c->rank ) NK( g_nccl.Send( base + m.off, ( size_t )m.cnt, ncclDouble, m.dst, c->comm, ls ) );
+          else NK( g_nccl.Recv( base + m.off, ( size_t )m.cnt, ncclDouble, m.src, c->comm, ls ) );
+        }
+        NK( g_nccl.GroupEnd() );
+        break; }
     }
     if ( l.record_ev >= 0 ) CK( cudaEventRecord( c->events[l.record_ev], ls ) );
     nlaunch++;
