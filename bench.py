@@ -14,8 +14,11 @@ Poisson 128^3 SPD system.  One "step" = factorize + evaluate(p=1) of that system
 
 `--impl reference` times the CPU implementation of the path (oracle port; the reference's own
 CHOLMOD/UMFPACK/MUMPS cannot be built in this image) on the same metric.
-N > 1 (torchrun): every rank factors its own replica on its own GPU (round 1: subtree sharding
-across GPUs is designed in DESIGN.md but not built yet) -- "scaling": "weak".
+N > 1 (torchrun, one rank per GPU): ONE factorization is spread over the N GPUs -- independent
+elimination-tree subtrees go to single ranks, the top separator fronts are distributed block-cyclically
+by column over rank groups, panels / contribution-block columns / finished factor panels move with NCCL
+over NVLink (csrc/host/b200_plan.c, DESIGN.md 7).  The problem size is fixed -> "scaling": "strong";
+value = F / (max over ranks of the device-timed factor seconds).
 """
 import argparse
 import ctypes as C
@@ -163,7 +166,10 @@ def main():
     # ---- problem + analysis (not timed: "analyze" is a separate tick in the reference, src/solvers.c:478)
     n, cp, ri, v = stencils.poisson3d_upper(args.grid)
     s = m.Solver(device=local)
-    t0 = time.perf_counter(); S = s.analyze(n, cp, ri, m.KIND_CHOLESKY); t_analyze = time.perf_counter() - t0
+    if world > 1:
+        s.join(rank, world, dist=dist)
+    host_threads = max(1, (os.cpu_count() or 8) // world)
+    t0 = time.perf_counter(); S = s.analyze(n, cp, ri, m.KIND_CHOLESKY, threads=host_threads); t_analyze = time.perf_counter() - t0
     F = S.flops
     ctx = s.ctx
     d_vals = L.b200_dev_alloc(ctx, v.nbytes); L.b200_dev_upload(ctx, d_vals, v.ctypes.data, v.nbytes)
@@ -209,7 +215,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         factor_s, solve_s, wall = t.tolist()
         tl = torch.tensor([launches], device="cuda", dtype=torch.int64); dist.all_reduce(tl); launches = int(tl.item())
-    value = world * F / factor_s / 1e9
+    value = F / factor_s / 1e9     # one factorization shared by all ranks (strong scaling)
 
     # correctness gate on the timed configuration: scaled backward error <= 1e-12
     x = np.empty(n); L.b200_dev_download(ctx, x.ctypes.data, d_x, x.nbytes)
@@ -218,11 +224,12 @@ def main():
     berr = float(np.abs(A @ x - bvec).max() / (12.0 * np.abs(x).max() + np.abs(bvec).max()))
 
     roofline = None; cpu_base = None; e2e = None; extra = {}
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream (profile mode serialises the launches;
+    # with N > 1 the factorization is collective, so every rank runs this pass and rank 0 reports its own kernels)
+    L.b200_set_profile(ctx, 1)
+    L.b200_factor_device(ctx, d_vals); L.b200_get_stats(ctx, C.byref(st))
+    L.b200_set_profile(ctx, 0)
     if rank == 0:
-        # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream (profile mode serialises the launches)
-        L.b200_set_profile(ctx, 1)
-        L.b200_factor_device(ctx, d_vals); L.b200_get_stats(ctx, C.byref(st))
-        L.b200_set_profile(ctx, 0)
         buf = C.create_string_buffer(4096); L.b200_get_profile(ctx, buf, 4096)
         prof = {l.split()[0]: (int(l.split()[1].split("=")[1]), float(l.split()[2].split("=")[1])) for l in buf.value.decode().strip().splitlines()}
         gemm_ms = st.gemm_ms; gemm_alg = st.gemm_alg_flops
@@ -243,7 +250,27 @@ def main():
     L.b200_dev_free(ctx, d_vals); L.b200_dev_free(ctx, d_b); L.b200_dev_free(ctx, d_x)
     s.close()
 
-    if rank == 0 and not args.no_e2e:
+    if world > 1 and not args.no_e2e:
+        # ---- e2e at N > 1: the C-ABI shim with HOST buffers on every rank (H2D of the values / b and D2H of x inside the timed calls);
+        # the plugin row itself is single-process (SOLVER_SINGLE_THREADED_ONLY), see DESIGN.md 7
+        s2 = m.Solver(device=local); s2.join(rank, world, dist=dist)
+        s2.analyze(n, cp, ri, m.KIND_CHOLESKY, threads=host_threads)
+        ftimes, etimes = [], []
+        for i in range(2 + 3):
+            dist.barrier(); t = time.perf_counter(); rc = s2.factor(v); tf = time.perf_counter() - t
+            t = time.perf_counter(); xe = s2.solve(bvec); te = time.perf_counter() - t
+            if rc != 0:
+                raise RuntimeError("factor failed: " + s2.err())
+            if i >= 2:
+                ftimes.append(tf); etimes.append(te)
+        import torch
+        tt = torch.tensor([float(np.mean(ftimes)), float(np.mean(etimes))], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        berr_e2e = float(np.abs(A @ xe - bvec).max() / (12.0 * np.abs(xe).max() + np.abs(bvec).max()))
+        s2.close()
+        e2e = {"value": F / tt[0].item() / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(world * (v.nbytes + bvec.nbytes)), "d2h_bytes_per_step": int(world * bvec.nbytes),
+               "factorize_s": tt[0].item(), "evaluate_s": tt[1].item(), "backward_error": berr_e2e,
+               "path": "b200_factor_host / b200_solve_host (C-ABI shim, pageable host buffers) on every rank, max over ranks"}
+    if world == 1 and rank == 0 and not args.no_e2e:
         # ---- e2e through the plugin table with host buffers (what `meagre-crowd -i A.mm -t -s b200` times)
         idx = L.lookup_solver_by_shortname(b"b200")
         A_m = m.make_matrix_csc(n, cp, ri, v, sym=m.SM_SYMMETRIC, location=m.UPPER_TRIANGULAR)
@@ -263,16 +290,16 @@ def main():
         e2e = {"value": F / float(np.mean(ftimes)) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(v.nbytes + bvec.nbytes), "d2h_bytes_per_step": int(bvec.nbytes),
                "factorize_s": float(np.mean(ftimes)), "evaluate_s": float(np.mean(etimes)), "backward_error": berr_e2e,
                "path": "solver_factorize/solver_evaluate via solver_lookup[] row 'b200', matrix_t in pageable host memory"}
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is reported at N=1 only
         r = cpu_factor_sample(m, args.cpu_grid)
         cpu_base = {"value": r["flops"] / r["best"] / 1e9, "unit": "GFLOP/s", "cores": r["cores"], "kind": "port",
                     "sample": f"poisson3d 7-pt {args.cpu_grid}^3 (n={r['n']}, F={r['flops']:.3e} flop), factorize {r['best']:.2f}s + solve {r['solve_s']:.2f}s, oracle multifrontal Cholesky, BLAS-3 via bundled OpenBLAS={r['blas']}, berr={r['berr']:.1e}"}
     if rank == 0:
         line = {"metric": "fp64_factor_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"poisson3d_7pt_{args.grid}^3_spd_cholesky", "step": "factorize + evaluate(p=1, automatic refinement), values and b resident in HBM",
                            "ordering": "nested dissection (own)", "l2": "inputs larger than L2 (factor touches >18 GB per step)",
-                           "multi_gpu": "replicas (one full problem per rank)" if world > 1 else "single GPU"},
+                           "multi_gpu": f"one factorization over {world} GPUs: subtrees -> ranks, top fronts 1-D block-cyclic, NCCL panels/contribution blocks" if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
         line.update(extra)
         print(json.dumps(line), flush=True)

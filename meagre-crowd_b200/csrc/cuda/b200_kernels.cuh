@@ -23,7 +23,6 @@
 namespace b200 {
 
 constexpr int NB = 64;        /* diagonal block / inner panel width */
-constexpr int POTRF_SMEM = ( 2 * NB * ( NB + 1 ) + NB ) * 8;
 constexpr int GETRF_SMEM = ( 3 * NB * ( NB + 1 ) + 2 * NB ) * 8;
 constexpr int TRSM_SMEM = ( NB * NB + NB * 128 ) * 8;
 
@@ -34,6 +33,7 @@ struct GemmTask {
   int M, N, K;
   int lower;   /* 1: store only elements with r + diag >= c */
   int diag;    /* (first row of C in the front) - (first col of C in the front) */
+  int mode;    /* 0: C -= A B' ;  1: C = A B' (panel rows times the inverse diagonal block; C may alias A when N, K <= 64) */
 };
 struct Tile { int task; unsigned short tm, tn; };
 
@@ -154,53 +154,82 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
 }
 
 /* ---------------------------------------------------- diagonal block: LL'
- * Right-looking Cholesky of an nb x nb (nb<=64) block held in shared memory,
- * then the inverse of the triangular factor (used by trsm_rows and the solves). */
-__global__ void __launch_bounds__( 256 ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
-  extern __shared__ double dsm[];
-  double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
-  double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
-  double* colv = dsm + 2 * NB * ( NB + 1 );
+ * Cholesky of an nb x nb (nb<=64) block, then the inverse of the triangular factor (used by the
+ * row update and the solves).  This kernel is the head of the dependency chain of every panel, so it
+ * is built for latency: 128 threads, the lane pair (2r, 2r+1) keeps row r of the block in registers
+ * (even / odd columns); one barrier per column -- every row publishes l(r,j) and its current
+ * a(r,j+1), from which all threads form the next pivot themselves; the inverse is formed column by
+ * column (a lane pair per column, partial sums joined by one shuffle) from the factor in shared memory. */
+constexpr int POTRF_THREADS = 128;
+__global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
+  constexpr int H = NB / 2;
+  __shared__ double Ls[NB][NB + 1];      /* finished factor, row-major             */
+  __shared__ double colv[2][NB];         /* l(:,j), double-buffered by j parity    */
+  __shared__ double nxt[2][NB];          /* a(:,j+1) before the update by column j */
+  __shared__ double rdiag[NB];           /* 1 / l(i,i)                             */
   const DiagTask t = tasks[blockIdx.x];
-  const int nb = t.nb, tid = threadIdx.x;
-  for ( int e = tid; e < nb * nb; e += 256 ) { int r = e % nb, c = e / nb; a[r][c] = ( r >= c ) ? t.A[r + ( int64_t )c * t.lda] : 0.0; x[r][c] = 0.0; }
+  const int nb = t.nb, r = threadIdx.x >> 1, h = threadIdx.x & 1;
+  double a[H];                           /* a[i] = A(r, 2i+h) */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) { const int c = 2 * i + h; a[i] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( c == r ? 1.0 : 0.0 ); }   /* beyond nb: identity */
+  if ( h == 0 ) nxt[0][r] = a[0];
   __syncthreads();
-  for ( int j = 0; j < nb; j++ ) {
-    double d = a[j][j];
-    if ( !( d > 0.0 ) ) { if ( tid == 0 ) atomicCAS( err, 0, t.col + j + 1 ); d = 1.0; }
-    const double s = sqrt( d );
-    if ( tid < nb ) colv[tid] = tid > j ? a[tid][j] / s : ( tid == j ? s : 0.0 );
-    __syncthreads();
-    if ( tid < nb && tid >= j ) a[tid][j] = colv[tid];
-    /* trailing update of the lower triangle, columns j+1.. */
-    const int r = tid & 63, cg = tid >> 6;
-    if ( r < nb && r > j ) {
-      const double lr = colv[r];
-      for ( int c = j + 1 + cg; c <= r; c += 4 ) a[r][c] -= lr * colv[c];
-    }
-    __syncthreads();
-  }
-  /* inverse of lower-triangular a: four lanes per column, split over q */
-  {
-    const int col = tid >> 2, part = tid & 3;
-    if ( col < nb ) {
-      if ( part == 0 ) x[col][col] = 1.0 / a[col][col];
-    }
-    __syncwarp();
-    for ( int i = 1; i < nb; i++ ) {
-      double s = 0.0;
-      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) s += a[i][q] * x[q][col];
-      s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-      s += __shfl_xor_sync( 0xffffffffu, s, 2 );
-      if ( col < nb && i > col && part == 0 ) x[i][col] = -s / a[i][i];
-      __syncwarp();
+  double dj = nxt[0][0];                 /* pivot of the current column, known to every thread */
+  bool bad = false;
+#pragma unroll
+  for ( int j = 0; j < NB; j++ ) {
+    if ( j < nb ) {                      /* uniform over the CTA: small blocks stop early */
+      if ( !( dj > 0.0 ) ) { bad = true; dj = 1.0; }
+      const double rs = rsqrt( dj );     /* one reciprocal square root per column; l = a * rs instead of a division */
+      const double sj = dj * rs;
+      if ( h == ( j & 1 ) ) {            /* the lane that holds column j of its row */
+        const double l = ( r > j ) ? a[j >> 1] * rs : ( r == j ? sj : 0.0 );
+        a[j >> 1] = l;
+        colv[j & 1][r] = l;
+        if ( r == j ) rdiag[j] = rs;
+      } else if ( j + 1 < NB ) nxt[( j + 1 ) & 1][r] = a[( j + 1 ) >> 1];
+      __syncthreads();
+      if ( j + 1 < NB ) {
+        const double* cv = colv[j & 1];
+        const double l = cv[r], ln = cv[j + 1];
+        dj = nxt[( j + 1 ) & 1][j + 1] - ln * ln;          /* next pivot */
+#pragma unroll
+        for ( int i = ( j + 1 ) >> 1; i < H; i++ ) { const int c = 2 * i + h; if ( c > j ) a[i] -= l * cv[c]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
+      }
+      if ( bad && threadIdx.x == 0 ) { atomicCAS( err, 0, t.col + j + 1 ); bad = false; }
     }
   }
+  /* store L, publish it row-major */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) {
+    const int c = 2 * i + h;
+    Ls[r][c] = ( c <= r ) ? a[i] : 0.0;
+    if ( r < nb && c <= r ) t.A[r + ( int64_t )c * t.lda] = a[i];
+  }
   __syncthreads();
-  for ( int e = tid; e < nb * nb; e += 256 ) {
-    int r = e % nb, c = e / nb;
-    if ( r >= c ) t.A[r + ( int64_t )c * t.lda] = a[r][c];
-    t.inv[r + c * nb] = x[r][c];
+  /* inverse X = inv(L): lane pair (c, h) owns column c;  x(c,c) = 1/l(c,c),  x(i,c) = -( sum_{q=c}^{i-1} l(i,q) x(q,c) ) / l(i,i);
+   * each lane keeps the x(q,c) with q = h (mod 2) and sums over those */
+  const int c = r;
+  double x[H];                           /* x[i] = X(2i+h, c) */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) x[i] = 0.0;
+#pragma unroll
+  for ( int i = 0; i < NB; i++ ) {
+    if ( i < nb ) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for ( int qi = 0; 2 * qi < i; qi += 2 ) {      /* rows q = 2qi+h < i; x(q,c) = 0 for q < c, so no predicate on c */
+        if ( 2 * qi + h < i ) s0 += Ls[i][2 * qi + h] * x[qi];
+        if ( 2 * ( qi + 1 ) + h < i ) s1 += Ls[i][2 * ( qi + 1 ) + h] * x[qi + 1];
+      }
+      double sum = s0 + s1;
+      sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
+      if ( h == ( i & 1 ) ) x[i >> 1] = ( i == c ) ? rdiag[i] : ( i > c ? -sum * rdiag[i] : 0.0 );
+    }
+  }
+  if ( c < nb ) {
+#pragma unroll
+    for ( int i = 0; i < H; i++ ) { const int row = 2 * i + h; if ( row < nb ) t.inv[row + c * nb] = x[i]; }
   }
 }
 
@@ -455,7 +484,7 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma
 #pragma unroll
         for ( int i = 0; i < MT; i++ ) {
           const int r = m0 + wm0 + i * 8 + fr;
-          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) cc[r] -= acc[i][j][h];
+          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
         }
       }
     }
@@ -585,7 +614,7 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt
 #pragma unroll
         for ( int i = 0; i < MT; i++ ) {
           const int r = m0 + wm0 + i * 8 + fr;
-          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) cc[r] -= acc[i][j][h];
+          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
         }
       }
     }

@@ -82,8 +82,8 @@ constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 
-enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_GEMM_SMALL, LK_NOP, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
-static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "gemm_dmma_unused", "nop", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
 /* one point-to-point message of the multi-GPU schedule: which = 0 L storage, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
 struct Msg { int src, dst, which; int64_t off, cnt; };
 
@@ -174,7 +174,6 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
   CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
   c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
-  CKN( cudaFuncSetAttribute( potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM ) );
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
@@ -239,7 +238,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
 static void add_gemm( std::vector<GemmTask>& tasks, std::vector<Tile>& big, std::vector<Tile>& small, double& flops,
                       double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N, int K, int lower, int diag ) {
   if ( M <= 0 || N <= 0 || K <= 0 ) return;
-  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = ldc; t.lda = lda; t.ldb = ldb; t.M = M; t.N = N; t.K = K; t.lower = lower; t.diag = diag;
+  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = ldc; t.lda = lda; t.ldb = ldb; t.M = M; t.N = N; t.K = K; t.lower = lower; t.diag = diag; t.mode = 0;
   const int id = ( int )tasks.size();
   tasks.push_back( t );
   if ( lower ) { const double nn = std::min( N, M + diag ); g_alg_flops += ( double )K * ( nn * ( nn + 1 ) + 2.0 * ( ( double )M + diag - nn ) * nn ); }
@@ -309,8 +308,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   CK( cudaMalloc( &c->dL, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
   if ( LU ) CK( cudaMalloc( &c->dU, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dCB[a], std::max<int64_t>( c->cb_arena[a], 2 ) * 8 ) );
-  CK( cudaMalloc( &c->dInv, std::max<int64_t>( invoff, 1 ) * 8 ) );
-  if ( LU ) { CK( cudaMalloc( &c->dInv2, std::max<int64_t>( invoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
+  CK( cudaMalloc( &c->dInv, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) );     /* + slack: the bulk copies of an odd-aligned block read one double past it */
+  if ( LU ) { CK( cudaMalloc( &c->dInv2, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
   CK( cudaMalloc( &c->dSinvF, std::max<int64_t>( sinvoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
   if ( LU ) CK( cudaMalloc( &c->dSinvTmp, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
@@ -400,7 +399,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( ( int64_t )dt.size() == d0 ) break;
         LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
         /* rows below the diagonal block */
-        const int64_t tl0 = ( int64_t )ttl.size();
+        const int64_t tl0 = ( int64_t )ttl.size(); std::vector<Tile> tbt;
         double tflops = 0;
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
@@ -409,18 +408,27 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           if ( below <= 0 ) continue;
           const double* inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB;
           const double* inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+          if ( nb == NB && c->use_bulk ) {   /* X = B T' on the tensor pipe: C = A B' with C = A = the rows below, B = the inverse diagonal block (in place: one CTA owns whole rows) */
+            double dummy = 0; const size_t ntask = gt.size();
+            double* Bp = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld;
+            add_gemm( gt, tbt, ts, dummy, Bp, m.ld, Bp, m.ld, LU ? inv2 : inv, nb, below, nb, nb, 0, 0 );
+            if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
+            tflops += ( double )below * nb * nb;
+          } else {
           TrsmTask x; x.B = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.ldb = m.ld; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr;
           int id = ( int )tt.size(); tt.push_back( x );
           for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
           tflops += ( double )below * nb * nb;
+          }
           if ( LU ) {
             TrsmTask y; y.B = Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0;
-            id = ( int )tt.size(); tt.push_back( y );
+            const int id = ( int )tt.size(); tt.push_back( y );
             for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
             tflops += ( double )below * nb * nb;
           }
         }
         if ( ( int64_t )ttl.size() > tl0 ) LS.push_back( { LK_TRSM, tl0, ( int64_t )ttl.size() - tl0, d, tflops } );
+        if ( !tbt.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt.size(), d, tflops } ); tb.insert( tb.end(), tbt.begin(), tbt.end() ); }
         /* update of the remaining columns of this outer panel */
         const int64_t b0 = ( int64_t )tb.size();
         double fb = 0;
@@ -677,11 +685,13 @@ static int run_factor( b200_ctx* c ) {
         break;
       case LK_DIAG:
         if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
-        else potrf_diag_kernel<<<( unsigned )l.count, 256, POTRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr );
+        else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
+      case LK_TRSM_MMA:
+        gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
+        break;
       case LK_GEMM_BIG:
-      case LK_GEMM_SMALL:
         if ( c->use_bulk ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
         else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
         gemm_flops += l.flops; gemm_launches++; break;
@@ -703,7 +713,9 @@ static int run_factor( b200_ctx* c ) {
       CK( cudaEventRecord( c->evp1, ls ) ); CK( cudaEventSynchronize( c->evp1 ) );
       float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->prof_ms[l.kind] += ms; c->prof_n[l.kind]++;
       static const bool trace = getenv( "B200_TRACE_GEMM" ) != nullptr;
-      if ( trace && ( l.kind == LK_GEMM_BIG || l.kind == LK_GEMM_SMALL ) && ms > 0.5f )
+      static const bool trace_all = getenv( "B200_TRACE_ALL" ) != nullptr;
+      if ( trace_all ) fprintf( stderr, "launch %s depth=%d count=%lld stream=%d ms=%.4f\n", kind_name[l.kind], l.depth, ( long long )l.count, l.stream, ms );
+      if ( trace && l.kind == LK_GEMM_BIG && ms > 0.5f )
         fprintf( stderr, "gemm depth=%d tiles=%lld flops=%.3e ms=%.3f TF/s=%.2f\n", l.depth, ( long long )l.count, l.flops, ms, l.flops / ( ms * 1e-3 ) / 1e12 );
     }
   }
@@ -718,7 +730,7 @@ static int run_factor( b200_ctx* c ) {
   float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
   c->stats.factor_ms = ms; c->stats.launches = nlaunch; c->stats.gemm_flops = gemm_flops; c->stats.gemm_launches = gemm_launches;
   c->stats.gemm_alg_flops = c->gemm_alg_flops * ( c->flops_stored > 0 ? c->flops_exact / c->flops_stored : 1.0 );
-  c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] + c->prof_ms[LK_GEMM_SMALL] : 0.0;
+  c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] : 0.0;
   c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes;
   if ( err != 0 ) { char a[64]; snprintf( a, 64, "%d", err - 1 ); set_err( "matrix is not positive definite (pivot column %s of the permuted matrix)%s", a, "" ); c->factored = false; return B200_ERR_NOT_SPD; }
   c->factored = true;
@@ -958,7 +970,7 @@ static double bench_variant( b200_ctx* c, int m, int n, int k, int iters ) {
   double *A, *B, *C;
   if ( cudaMalloc( &A, ( size_t )m * k * 8 ) || cudaMalloc( &B, ( size_t )n * k * 8 ) || cudaMalloc( &C, ( size_t )m * n * 8 ) ) return -1.0;
   cudaMemset( A, 0, ( size_t )m * k * 8 ); cudaMemset( B, 0, ( size_t )n * k * 8 ); cudaMemset( C, 0, ( size_t )m * n * 8 );
-  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = m; t.lda = m; t.ldb = n; t.M = m; t.N = n; t.K = k; t.lower = 0; t.diag = 0;
+  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = m; t.lda = m; t.ldb = n; t.M = m; t.N = n; t.K = k; t.lower = 0; t.diag = 0; t.mode = 0;
   std::vector<GemmTask> gt( 1, t ); std::vector<Tile> tl;
   for ( int tn = 0; tn * BN < n; tn++ ) for ( int tm = 0; tm * BM < m; tm++ ) { Tile x; x.task = 0; x.tm = ( unsigned short )tm; x.tn = ( unsigned short )tn; tl.push_back( x ); }
   DevVec<GemmTask> dgt; DevVec<Tile> dtl; dgt.upload( gt ); dtl.upload( tl );
