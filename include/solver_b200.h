@@ -166,13 +166,13 @@ int b200_plan_col_owner( const b200_plan_t* pl, const b200_symbolic_t* S, int s,
 int b200_plan_member( const b200_plan_t* pl, int s, int r );
 int64_t b200_plan_cb_transfers( const b200_plan_t* pl, const b200_symbolic_t* S, int depth, b200_xfer_t* out, int64_t cap );
 
-/* multi-process mode (one process per GPU, e.g. under torchrun): rank 0 creates a 128-byte NCCL id,
+/* multi-process mode (one process per GPU, e.g. under torchrun): rank 0 creates two NCCL ids (256 bytes: one communicator for panels, one for bulk factor replication),
  * the launcher hands it to every rank (bench.py: torch.distributed broadcast), and each rank joins
  * BEFORE b200_upload_symbolic.  Panels of distributed fronts and contribution-block columns at subtree
  * boundaries then move with NCCL over NVLink inside b200_factor_*; afterwards every rank holds the
  * whole factor and b200_solve_* works on any of them. */
-int b200_mg_unique_id( char* out128 );
-int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id128 );
+int b200_mg_unique_id( char* out256 );
+int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id256 );
 int b200_mg_rank( b200_ctx_t* c, int* rank, int* world );
 
 /* iterative refinement: r = b - A x is accumulated in double-double on the device, then one more

@@ -277,19 +277,19 @@ class Solver:
     def err(self):
         return self.L.b200_last_error().decode()
 
-    def join(self, rank, world, id128=None, dist=None):
-        """multi-process mode: one rank per GPU.  Either pass the 128-byte NCCL id, or a torch.distributed
+    def join(self, rank, world, id256=None, dist=None):
+        """multi-process mode: one rank per GPU.  Either pass the 256 bytes of b200_mg_unique_id, or a torch.distributed
         module with an initialised process group (rank 0 creates the id and broadcasts it)."""
-        if world > 1 and id128 is None:
+        if world > 1 and id256 is None:
             import torch
-            buf = C.create_string_buffer(128)
+            buf = C.create_string_buffer(256)
             if rank == 0 and self.L.b200_mg_unique_id(buf) != B200_OK:
                 raise RuntimeError("b200_mg_unique_id: " + self.err())
             dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
             t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
             dist.broadcast(t, src=0)
-            id128 = bytes(t.cpu().tolist())
-        r = self.L.b200_mg_init(self.ctx, rank, world, id128)
+            id256 = bytes(t.cpu().tolist())
+        r = self.L.b200_mg_init(self.ctx, rank, world, id256)
         if r != B200_OK:
             raise RuntimeError("b200_mg_init: " + self.err())
 

@@ -111,8 +111,8 @@ template <class T> struct DevVec {
 
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
-  int rank = 0, world = 1; ncclComm_t comm = nullptr; b200_plan_t* plan = nullptr; std::vector<Msg> msgs; double comm_bytes = 0;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  int rank = 0, world = 1; ncclComm_t comm = nullptr, comm2 = nullptr;   /* comm/stream3: latency-critical panel and contribution-block traffic; comm2/stream4: bulk factor replication */ b200_plan_t* plan = nullptr; std::vector<Msg> msgs; double comm_bytes = 0;
   std::vector<cudaEvent_t> events; int nevents = 0;
   cudaDeviceProp prop;
   /* symbolic copy */
@@ -153,6 +153,7 @@ struct b200_ctx {
   double tiny = 0.0;
   b200_stats_t stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evs = nullptr;
+  std::vector<cudaEvent_t> lvl_ev; std::vector<float> lvl_ms;   /* update-stream time stamps at level boundaries (diagnostics) */
   int64_t device_bytes = 0;
 };
 
@@ -167,7 +168,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->device = device;
   CKN( cudaGetDeviceProperties( &c->prop, device ) );
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
-    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); }
+    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); }
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
@@ -183,25 +184,27 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
 
 
 /* ------------------------------------------------------------ multi-process mode */
-extern "C" int b200_mg_unique_id( char* out128 ) {
-  if ( !out128 ) return B200_ERR_ARG;
+extern "C" int b200_mg_unique_id( char* out256 ) {
+  if ( !out256 ) return B200_ERR_ARG;
   if ( load_nccl() ) return B200_ERR_CUDA;
-  ncclUniqueId id; static_assert( sizeof( ncclUniqueId ) == 128, "NCCL id is 128 bytes" );
-  NK( g_nccl.GetUniqueId( &id ) );
-  memcpy( out128, &id, 128 );
+  static_assert( sizeof( ncclUniqueId ) == 128, "NCCL id is 128 bytes" );
+  for ( int k = 0; k < 2; k++ ) { ncclUniqueId id; NK( g_nccl.GetUniqueId( &id ) ); memcpy( out256 + 128 * k, &id, 128 ); }   /* one id per communicator */
   return B200_OK;
 }
-extern "C" int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id128 ) {
+extern "C" int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id256 ) {
   if ( !c || world < 1 || rank < 0 || rank >= world ) return B200_ERR_ARG;
   if ( c->dL ) { set_err( "b200_mg_init must precede b200_upload_symbolic%s", "" ); return B200_ERR_STATE; }
   CK( cudaSetDevice( c->device ) );
   if ( c->comm ) { g_nccl.CommDestroy( c->comm ); c->comm = nullptr; }
+  if ( c->comm2 ) { g_nccl.CommDestroy( c->comm2 ); c->comm2 = nullptr; }
   c->rank = rank; c->world = world;
   if ( world == 1 ) return B200_OK;
-  if ( !id128 ) return B200_ERR_ARG;
+  if ( !id256 ) return B200_ERR_ARG;
   if ( load_nccl() ) return B200_ERR_CUDA;
-  ncclUniqueId id; memcpy( &id, id128, 128 );
+  ncclUniqueId id; memcpy( &id, id256, 128 );
   NK( g_nccl.CommInitRank( &c->comm, world, id, rank ) );
+  memcpy( &id, id256 + 128, 128 );
+  NK( g_nccl.CommInitRank( &c->comm2, world, id, rank ) );
   return B200_OK;
 }
 extern "C" int b200_mg_rank( b200_ctx_t* c, int* rank, int* world ) { if ( !c ) return B200_ERR_ARG; if ( rank ) *rank = c->rank; if ( world ) *world = c->world; return B200_OK; }
@@ -228,9 +231,11 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
+  for ( cudaEvent_t e : c->lvl_ev ) cudaEventDestroy( e );
   if ( c->comm ) g_nccl.CommDestroy( c->comm );
+  if ( c->comm2 ) g_nccl.CommDestroy( c->comm2 );
   if ( c->plan ) b200_plan_free( c->plan );
-  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 ); cudaStreamDestroy( c->stream3 );
+  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 ); cudaStreamDestroy( c->stream3 ); cudaStreamDestroy( c->stream4 );
   delete c;
 }
 
@@ -340,12 +345,36 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   auto new_event = [&]() { return c->nevents++; };
   /* join helpers: make stream `to` wait for everything issued so far on stream `from` */
   auto push_nop = [&]( int d, int stream ) { Launch l = { LK_NOP, 0, 0, d, 0.0 }; l.stream = stream; LS.push_back( l ); };
+  /* runs of supernodes with the same holders (contiguous in L storage) and the level after which they are final */
+  struct Run { int s0, s1, h0, hn, ready; };
+  std::vector<Run> runs; int ev_bulk_last = -1;
+  if ( MG ) {
+    int s0 = 0;
+    while ( s0 < ns ) {
+      if ( pl->dist[s0] ) { runs.push_back( { s0, s0, pl->grp_first[s0], pl->grp_size[s0], meta[s0].depth } ); s0++; continue; }
+      int s1 = s0, dmin = meta[s0].depth;
+      while ( s1 + 1 < ns && !pl->dist[s1 + 1] && pl->grp_first[s1 + 1] == pl->grp_first[s0] ) { s1++; dmin = std::min( dmin, meta[s1].depth ); }
+      runs.push_back( { s0, s1, pl->grp_first[s0], 1, dmin } );
+      s0 = s1 + 1;
+    }
+  }
   for ( int d = S->maxdepth; d >= 0; d-- ) {
     std::vector<int> lv;                                     /* the supernodes of this level I take part in */
     int maxf_all = 0;
     for ( int s : levels[d] ) { maxf_all = std::max( maxf_all, meta[s].f ); if ( member( s ) ) lv.push_back( s ); }
     double* CB = c->dCB[d & 1];
-    if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, d & 1, c->level_cb[d], d, 0.0 } );
+    if ( !MG ) { if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, 0, c->level_cb[d], d, 0.0 } ); }
+    else { /* zero only the contribution blocks I will write: merge neighbouring ranges of the arena */
+      int64_t lo = -1, hi = -1;
+      for ( int s : lv ) {
+        const int64_t u = meta[s].f - meta[s].k; if ( u == 0 ) continue;
+        const int64_t a = meta[s].cbptr, b = a + ( ( u + 1 ) & ~( int64_t )1 ) * u;
+        if ( lo >= 0 && a <= hi + 4096 ) { hi = std::max( hi, b ); continue; }
+        if ( lo >= 0 ) LS.push_back( { LK_MEMSET_CB, lo, hi - lo, d, 0.0 } );
+        lo = a; hi = b;
+      }
+      if ( lo >= 0 ) LS.push_back( { LK_MEMSET_CB, lo, hi - lo, d, 0.0 } );
+    }
     if ( MG ) { /* contribution-block columns computed elsewhere that my part of this level's fronts needs, and vice versa */
       const int64_t nx = b200_plan_cb_transfers( pl, S, d, nullptr, 0 );
       if ( nx > 0 ) {
@@ -384,6 +413,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
     for ( int J = 0; J < maxk; J += NBO ) {
       const size_t panel_first = LS.size();
+      int ev_fwd_last = -1;                 /* last per-block panel piece I received as the owner of the next panel */
       for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
         const int64_t d0 = ( int64_t )dt.size();
         for ( int s : lv ) {
@@ -396,8 +426,9 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
           dt.push_back( x );
         }
-        if ( ( int64_t )dt.size() == d0 ) break;
-        LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
+        const bool have_diag = ( int64_t )dt.size() > d0;
+        if ( !have_diag && !any_dist ) break;
+        if ( have_diag ) LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
         /* rows below the diagonal block */
         const int64_t tl0 = ( int64_t )ttl.size(); std::vector<Tile> tbt;
         double tflops = 0;
@@ -429,6 +460,29 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         }
         if ( ( int64_t )ttl.size() > tl0 ) LS.push_back( { LK_TRSM, tl0, ( int64_t )ttl.size() - tl0, d, tflops } );
         if ( !tbt.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt.size(), d, tflops } ); tb.insert( tb.end(), tbt.begin(), tbt.end() ); }
+        if ( any_dist ) { /* the 64 columns just finished go straight to the owner of the NEXT panel, while the rest of this panel is
+                           * still being factored: only the last block's transfer stays on the critical path */
+          const int64_t m0 = ( int64_t )MS.size(); bool i_recv = false, i_send = false;
+          for ( int s : lv ) {
+            const SnMeta& m = meta[s];
+            if ( !is_dist( s ) || j0 >= m.k ) continue;
+            const int root = b200_plan_col_owner( pl, S, s, J ), nxt = J + NBO < m.k ? b200_plan_col_owner( pl, S, s, J + NBO ) : -1;
+            if ( nxt < 0 || nxt == root || ( me != root && me != nxt ) ) continue;
+            const int nb = std::min( NB, m.k - j0 );
+            MS.push_back( { root, nxt, 0, m.lptr + ( int64_t )j0 * m.ld, ( int64_t )nb * m.ld } );
+            MS.push_back( { root, nxt, 1, m.invptr + ( int64_t )( j0 / NB ) * NB * NB, ( int64_t )nb * nb } );
+            c->comm_bytes += ( double )nb * m.ld * 8.0;
+            if ( me == nxt ) i_recv = true; else i_send = true;
+          }
+          if ( ( int64_t )MS.size() > m0 ) {
+            int wait = -1;
+            if ( i_send ) { wait = new_event(); LS.back().record_ev = wait; }     /* LS.back(): my last compute launch of this block (row update, or the diagonal block) */
+            Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = wait; l.record_ev = new_event();
+            LS.push_back( l );
+            if ( i_recv ) ev_fwd_last = l.record_ev;
+          }
+        }
+        if ( !have_diag ) continue;
         /* update of the remaining columns of this outer panel */
         const int64_t b0 = ( int64_t )tb.size();
         double fb = 0;
@@ -449,27 +503,41 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( ( int64_t )tb.size() > b0 ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } ); LS.back().flops += fb; }
       }
       int ev_panel = -1;
-      if ( look && LS.size() > panel_first ) {
-        for ( size_t q = panel_first; q < LS.size(); q++ ) LS[q].stream = 1;
-        LS[panel_first].wait_ev = ev_next;
-        LS.back().record_ev = c->nevents; ev_panel = c->nevents++;
-      }
-      if ( any_dist ) { /* the factored panels (and their diagonal-block inverses) go from their owner to the rest of the group */
-        const int64_t m0 = ( int64_t )MS.size();
-        for ( int s : lv ) {
-          const SnMeta& m = meta[s];
-          if ( !is_dist( s ) || J >= m.k ) continue;
-          const int root = b200_plan_col_owner( pl, S, s, J ); const int kb = std::min( NBO, m.k - J );
-          for ( int r = pl->grp_first[s]; r < pl->grp_first[s] + pl->grp_size[s]; r++ ) {
-            if ( r == root || ( me != root && me != r ) ) continue;
-            MS.push_back( { root, r, 0, m.lptr + ( int64_t )J * m.ld, ( int64_t )kb * m.ld } );
-            MS.push_back( { root, r, 1, m.invptr + ( int64_t )( J / NB ) * NB * NB, ( int64_t )( kb / NB ) * NB * NB + ( int64_t )( kb % NB ) * ( kb % NB ) } );
-            c->comm_bytes += ( double )kb * m.ld * 8.0;
-          }
+      if ( look ) { /* my compute launches of this panel go to the panel stream */
+        int qf = -1, ql = -1;
+        for ( size_t q = panel_first; q < LS.size(); q++ ) if ( LS[q].stream == 0 ) { LS[q].stream = 1; if ( qf < 0 ) qf = ( int )q; ql = ( int )q; }
+        if ( qf >= 0 ) {
+          LS[qf].wait_ev = ev_next;
+          if ( LS[ql].record_ev < 0 ) LS[ql].record_ev = c->nevents++;
+          ev_panel = LS[ql].record_ev;
         }
-        if ( ( int64_t )MS.size() > m0 ) {
-          Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = ev_panel; l.record_ev = c->nevents; ev_panel = c->nevents++;
-          LS.push_back( l );
+      }
+      if ( any_dist ) { /* the factored panels (and their diagonal-block inverses) go from their owner to the rest of the group:
+                         * first to the owner of the NEXT panel -- the only copy the critical path waits for -- then to the others.
+                         * The owner itself goes on as soon as its panel is done (its sends only read the panel). */
+        const int ev_pdone = ev_panel;
+        if ( ev_fwd_last >= 0 ) ev_panel = ev_fwd_last;       /* I own the next panel: I have it all once the last block has arrived */
+        {
+          const int64_t m0 = ( int64_t )MS.size();
+          bool i_receive = false;
+          for ( int s : lv ) {
+            const SnMeta& m = meta[s];
+            if ( !is_dist( s ) || J >= m.k ) continue;
+            const int root = b200_plan_col_owner( pl, S, s, J ); const int kb = std::min( NBO, m.k - J );
+            const int nxt = J + NBO < m.k ? b200_plan_col_owner( pl, S, s, J + NBO ) : -1;
+            for ( int r = pl->grp_first[s]; r < pl->grp_first[s] + pl->grp_size[s]; r++ ) {
+              if ( r == root || r == nxt || ( me != root && me != r ) ) continue;
+              MS.push_back( { root, r, 0, m.lptr + ( int64_t )J * m.ld, ( int64_t )kb * m.ld } );
+              MS.push_back( { root, r, 1, m.invptr + ( int64_t )( J / NB ) * NB * NB, ( int64_t )( kb / NB ) * NB * NB + ( int64_t )( kb % NB ) * ( kb % NB ) } );
+              c->comm_bytes += ( double )kb * m.ld * 8.0;
+              if ( me == r ) i_receive = true;
+            }
+          }
+          if ( ( int64_t )MS.size() > m0 ) {
+            Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = ev_pdone; l.record_ev = c->nevents++;
+            LS.push_back( l );
+            if ( i_receive ) ev_panel = l.record_ev;
+          }
         }
       }
       /* trailing update with the whole outer panel, in two launches: first the columns of the NEXT
@@ -529,34 +597,30 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         }
       }
     }
-  }
-  if ( MG ) { /* every rank ends up with the whole factor (L panels and diagonal-block inverses): holders send what the others lack */
-    const int64_t m0 = ( int64_t )MS.size();
-    auto emit = [&]( int s0, int s1, int h0, int hn ) {     /* supernodes s0..s1 held by ranks [h0, h0+hn) */
-      const int64_t lo = meta[s0].lptr, lcnt = S->lptr[s1 + 1] - lo;
-      const int64_t io = meta[s0].invptr, icnt = ( s1 + 1 < ns ? meta[s1 + 1].invptr : c->invsize ) - io;
-      for ( int r = 0; r < c->world; r++ ) {
-        if ( r >= h0 && r < h0 + hn ) continue;
-        if ( me != h0 && me != r ) continue;
-        if ( lcnt > 0 ) { MS.push_back( { h0, r, 0, lo, lcnt } ); c->comm_bytes += ( double )lcnt * 8.0; }
-        if ( icnt > 0 ) MS.push_back( { h0, r, 1, io, icnt } );
+    if ( MG ) { /* replicate what has become final on this level: every rank ends up with the whole factor (L panels and
+                 * diagonal-block inverses) for the sweeps.  Bulk traffic has its own communicator and stream so that it
+                 * never queues in front of a panel on the critical path. */
+      const int64_t m0 = ( int64_t )MS.size();
+      for ( const Run& rn : runs ) {
+        if ( rn.ready != d ) continue;
+        const int64_t lo = meta[rn.s0].lptr, lcnt = S->lptr[rn.s1 + 1] - lo;
+        const int64_t io = meta[rn.s0].invptr, icnt = ( rn.s1 + 1 < ns ? meta[rn.s1 + 1].invptr : c->invsize ) - io;
+        for ( int r = 0; r < c->world; r++ ) {
+          if ( r >= rn.h0 && r < rn.h0 + rn.hn ) continue;
+          if ( me != rn.h0 && me != r ) continue;
+          if ( lcnt > 0 ) { MS.push_back( { rn.h0, r, 0, lo, lcnt } ); c->comm_bytes += ( double )lcnt * 8.0; }
+          if ( icnt > 0 ) MS.push_back( { rn.h0, r, 1, io, icnt } );
+        }
       }
-    };
-    int s0 = 0;
-    while ( s0 < ns ) {
-      if ( pl->dist[s0] ) { emit( s0, s0, pl->grp_first[s0], pl->grp_size[s0] ); s0++; continue; }
-      int s1 = s0;
-      while ( s1 + 1 < ns && !pl->dist[s1 + 1] && pl->grp_first[s1 + 1] == pl->grp_first[s0] ) s1++;
-      emit( s0, s1, pl->grp_first[s0], 1 );
-      s0 = s1 + 1;
-    }
-    if ( ( int64_t )MS.size() > m0 ) {
-      const int ea = new_event(), eb = new_event();
-      push_nop( 0, 0 ); LS.back().record_ev = ea;
-      Launch l = { LK_GATHER, m0, ( int64_t )MS.size() - m0, 0, 0.0 }; l.stream = 2; l.wait_ev = ea; l.record_ev = eb; LS.push_back( l );
-      push_nop( 0, 0 ); LS.back().wait_ev = eb;
+      if ( ( int64_t )MS.size() > m0 ) {
+        const int ea = new_event();
+        push_nop( d, 0 ); LS.back().record_ev = ea;
+        Launch l = { LK_GATHER, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 3; l.wait_ev = ea; l.record_ev = new_event(); ev_bulk_last = l.record_ev;
+        LS.push_back( l );
+      }
     }
   }
+  if ( MG && ev_bulk_last >= 0 ) { push_nop( 0, 0 ); LS.back().wait_ev = ev_bulk_last; }     /* the factor is complete on this rank once the bulk channel has drained */
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
 
@@ -669,16 +733,21 @@ static int run_factor( b200_ctx* c ) {
     const int blocks = ( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 16 );
     scatter_A_kernel<<<blocks, 256, 0, st>>>( c->dVals, c->amap.d, c->nnzA, c->dL, c->dU );
   }
-  if ( c->world > 1 ) { CK( cudaEventRecord( c->evs, st ) ); CK( cudaStreamWaitEvent( c->stream3, c->evs, 0 ) ); }   /* nothing may land in L before it has been zeroed and scattered */
+  if ( c->world > 1 ) { CK( cudaEventRecord( c->evs, st ) ); CK( cudaStreamWaitEvent( c->stream3, c->evs, 0 ) ); CK( cudaStreamWaitEvent( c->stream4, c->evs, 0 ) ); }   /* nothing may land in L before it has been zeroed and scattered */
   int64_t nlaunch = 3 + ( LU ? 1 : 0 );
   double gemm_flops = 0; int64_t gemm_launches = 0;
   for ( int k = 0; k < LK_COUNT; k++ ) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+  int cur_depth = -1; size_t nlev = 0;
   for ( const Launch& l : c->launches ) {
-    cudaStream_t ls = l.stream == 0 ? c->stream : l.stream == 1 ? c->stream2 : c->stream3;
+    if ( l.stream == 0 && l.depth != cur_depth ) {   /* time stamp on the update stream when a new tree level begins */
+      if ( c->lvl_ev.size() <= nlev ) { cudaEvent_t e; CK( cudaEventCreate( &e ) ); c->lvl_ev.push_back( e ); }
+      CK( cudaEventRecord( c->lvl_ev[nlev++], c->stream ) ); cur_depth = l.depth;
+    }
+    cudaStream_t ls = l.stream == 0 ? c->stream : l.stream == 1 ? c->stream2 : l.stream == 2 ? c->stream3 : c->stream4;
     if ( l.wait_ev >= 0 ) CK( cudaStreamWaitEvent( ls, c->events[l.wait_ev], 0 ) );
     if ( c->profile ) CK( cudaEventRecord( c->evp0, ls ) );
     switch ( l.kind ) {
-      case LK_MEMSET_CB: CK( cudaMemsetAsync( c->dCB[l.first], 0, ( size_t )l.count * 8, ls ) ); break;
+      case LK_MEMSET_CB: CK( cudaMemsetAsync( c->dCB[l.depth & 1] + l.first, 0, ( size_t )l.count * 8, ls ) ); break;
       case LK_ASM:
         if ( LU ) extend_add_kernel<true><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
         else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
@@ -701,8 +770,9 @@ static int run_factor( b200_ctx* c ) {
         for ( int64_t i = l.first; i < l.first + l.count; i++ ) {
           const Msg& m = c->msgs[i];
           double* base = m.which == 0 ? c->dL : m.which == 1 ? c->dInv : c->dCB[m.which - 2];
-          if ( m.src == c->rank ) NK( g_nccl.Send( base + m.off, ( size_t )m.cnt, ncclDouble, m.dst, c->comm, ls ) );
-          else NK( g_nccl.Recv( base + m.off, ( size_t )m.cnt, ncclDouble, m.src, c->comm, ls ) );
+          ncclComm_t cm = l.stream == 3 ? c->comm2 : c->comm;
+          if ( m.src == c->rank ) NK( g_nccl.Send( base + m.off, ( size_t )m.cnt, ncclDouble, m.dst, cm, ls ) );
+          else NK( g_nccl.Recv( base + m.off, ( size_t )m.cnt, ncclDouble, m.src, cm, ls ) );
         }
         NK( g_nccl.GroupEnd() );
         break; }
@@ -728,6 +798,8 @@ static int run_factor( b200_ctx* c ) {
   CK( cudaMemcpyAsync( &pert, c->dPert, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
   CK( cudaStreamSynchronize( st ) );
   float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
+  c->lvl_ms.assign( nlev, 0.f );
+  for ( size_t i = 0; i < nlev; i++ ) { cudaEvent_t nx = i + 1 < nlev ? c->lvl_ev[i + 1] : c->ev1; cudaEventElapsedTime( &c->lvl_ms[i], c->lvl_ev[i], nx ); }
   c->stats.factor_ms = ms; c->stats.launches = nlaunch; c->stats.gemm_flops = gemm_flops; c->stats.gemm_launches = gemm_launches;
   c->stats.gemm_alg_flops = c->gemm_alg_flops * ( c->flops_stored > 0 ? c->flops_exact / c->flops_stored : 1.0 );
   c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] : 0.0;
@@ -922,6 +994,8 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
   static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_first", "solve_fwd_step", "solve_bwd_step" };
   for ( int k = 0; k < SK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", sname[k], ( long long )c->sprof_n[k], c->sprof_ms[k] ); s += line; }
+  { float t0 = 0; if ( !c->lvl_ev.empty() ) cudaEventElapsedTime( &t0, c->ev0, c->lvl_ev[0] ); snprintf( line, sizeof( line ), "levels_ms(deepest first; prologue %.2f):", t0 ); s += line;
+    for ( float v : c->lvl_ms ) { snprintf( line, sizeof( line ), " %.2f", v ); s += line; } s += "\n"; }
   snprintf( buf, len, "%s", s.c_str() );
   return B200_OK;
 }

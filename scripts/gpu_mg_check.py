@@ -26,6 +26,12 @@ for it in range(reps):
     tt = torch.tensor([st.factor_ms], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"[world {world}] grid={grid} factor max-over-ranks={tt.item():.2f} ms ({S.flops / tt.item() / 1e9:.2f} TF/s) wall={tf * 1e3:.1f} ms solve={st2.solve_ms:.2f} ms launches={st.launches}", flush=True)
+cb = C.create_string_buffer(8192); s.L.b200_get_profile(s.ctx, cb, 8192)
+lv = [l for l in cb.value.decode().splitlines() if l.startswith("levels_ms")]
+for r_ in range(world):
+    dist.barrier()
+    if r_ == rank and lv:
+        t = lv[0].split(":")[1].split(); print(f"rank {rank} level ms (root last): ... " + " ".join(t[-8:]) + f" | sum {sum(float(x) for x in t):.1f}", flush=True)
 A = stencils.to_scipy(n, cp, ri, v, True)
 berr = float(np.abs(A @ x - b).max() / (12.0 * np.abs(x).max() + np.abs(b).max()))
 Lmg = s.read_factor(0)
