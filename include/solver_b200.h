@@ -212,6 +212,7 @@ double b200_bench_dgemm_variant( b200_ctx_t* c, int variant, int m, int n, int k
 double b200_bench_dmma_occupancy( b200_ctx_t* c, int warps_per_sm, int ilp );   /* DMMA rate vs resident warps / independent accumulators */
 double b200_bench_fp64_peak_tflops( b200_ctx_t* c, int which, int iters );  /* 0: DMMA.8x8x4 issue roof, 1: DFMA roof */
 double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters );
+double b200_bench_potrf_us( b200_ctx_t* c, int which, int nb, int ntasks, int iters );   /* diagonal-block kernels: 0 unrolled/registers, 1 rolled/shared memory */
 
 #ifdef __cplusplus
 }

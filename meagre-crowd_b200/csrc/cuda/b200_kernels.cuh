@@ -233,6 +233,56 @@ __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const Diag
   }
 }
 
+/* The same operation with rolled loops and the block in shared memory: a few hundred instructions instead of
+ * ~12 000, so nothing streams through the instruction cache.  Used for blocks narrower than NB (the many small
+ * supernodes of the deep tree levels), where the unrolled kernel above would mostly skip over its own code.
+ * One barrier per column: column j stays unscaled in place (it is never read again), every thread rescales what
+ * it needs with rs = 1/sqrt(a(j,j)); a final pass turns the columns into L. */
+constexpr int POTRF_S_SMEM = ( 2 * NB * ( NB + 1 ) + NB ) * 8;
+__global__ void __launch_bounds__( 256 ) potrf_diag_small_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
+  extern __shared__ double dsm[];
+  double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
+  double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
+  double* rsv = dsm + 2 * NB * ( NB + 1 );
+  const DiagTask t = tasks[blockIdx.x];
+  const int nb = t.nb, tid = threadIdx.x;
+  for ( int e = tid; e < nb * nb; e += 256 ) { const int r = e % nb, c = e / nb; a[r][c] = ( r >= c ) ? t.A[r + ( int64_t )c * t.lda] : 0.0; x[r][c] = 0.0; }
+  __syncthreads();
+  const int r = tid & ( NB - 1 ), cg = tid >> 6;
+  for ( int j = 0; j < nb; j++ ) {
+    double d = a[j][j];
+    if ( !( d > 0.0 ) ) { if ( tid == 0 ) atomicCAS( err, 0, t.col + j + 1 ); d = 1.0; }
+    const double rs = rsqrt( d );
+    if ( tid == 0 ) rsv[j] = rs;
+    if ( r > j && r < nb ) {
+      const double lr = a[r][j] * rs * rs;            /* l(r,j) / sqrt(d): the other factor a(c,j) is taken unscaled */
+      for ( int c = j + 1 + cg; c <= r; c += 4 ) a[r][c] -= lr * a[c][j];
+    }
+    __syncthreads();
+  }
+  for ( int e = tid; e < nb * nb; e += 256 ) { const int rr = e % nb, c = e / nb; if ( rr >= c ) a[rr][c] = ( rr == c ) ? a[rr][c] * rsv[c] : a[rr][c] * rsv[c]; }   /* column c of L = a(:,c) * rs(c) */
+  __syncthreads();
+  {
+    const int col = tid >> 2, part = tid & 3;
+    if ( col < nb && part == 0 ) x[col][col] = rsv[col];
+    __syncwarp();
+    for ( int i = 1; i < nb; i++ ) {
+      double s = 0.0;
+      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) s += a[i][q] * x[q][col];
+      s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+      s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+      if ( col < nb && i > col && part == 0 ) x[i][col] = -s * rsv[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for ( int e = tid; e < nb * nb; e += 256 ) {
+    const int rr = e % nb, c = e / nb;
+    if ( rr >= c ) t.A[rr + ( int64_t )c * t.lda] = a[rr][c];
+    t.inv[rr + c * nb] = x[rr][c];
+  }
+}
+
 /* ------------------------------------------------------ diagonal block: LU
  * LU of an nb x nb block with partial pivoting restricted to the block's own
  * rows.  piv[j] = block-local row swapped into position j.  Tiny pivots are

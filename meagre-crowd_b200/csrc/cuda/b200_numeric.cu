@@ -82,8 +82,8 @@ constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 
-enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
-static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_DIAG_S, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "diag_block_small", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
 /* one point-to-point message of the multi-GPU schedule: which = 0 L storage, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
 struct Msg { int src, dst, which; int64_t off, cnt; };
 
@@ -176,6 +176,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
   c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
+  CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
   memset( &c->stats, 0, sizeof( c->stats ) );
@@ -415,20 +416,26 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
       const size_t panel_first = LS.size();
       int ev_fwd_last = -1;                 /* last per-block panel piece I received as the owner of the next panel */
       for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
-        const int64_t d0 = ( int64_t )dt.size();
-        for ( int s : lv ) {
-          const SnMeta& m = meta[s];
-          if ( j0 >= m.k || !owns( s, J ) ) continue;
-          const int nb = std::min( NB, m.k - j0 );
-          DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
-          x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
-          x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
-          x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
-          dt.push_back( x );
+        const int64_t d0 = ( int64_t )dt.size(); int64_t d1 = d0;
+        for ( int pass = 0; pass < 2; pass++ ) {           /* full 64-column blocks first (unrolled register kernel), then the narrower ones */
+          for ( int s : lv ) {
+            const SnMeta& m = meta[s];
+            if ( j0 >= m.k || !owns( s, J ) ) continue;
+            const int nb = std::min( NB, m.k - j0 );
+            if ( !LU && ( pass == 0 ) != ( nb == NB ) ) continue;
+            if ( LU && pass == 1 ) continue;
+            DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
+            x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
+            x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+            x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
+            dt.push_back( x );
+          }
+          if ( pass == 0 ) d1 = ( int64_t )dt.size();
         }
         const bool have_diag = ( int64_t )dt.size() > d0;
         if ( !have_diag && !any_dist ) break;
-        if ( have_diag ) LS.push_back( { LK_DIAG, d0, ( int64_t )dt.size() - d0, d, 0.0 } );
+        if ( d1 > d0 ) LS.push_back( { LK_DIAG, d0, d1 - d0, d, 0.0 } );
+        if ( ( int64_t )dt.size() > d1 ) LS.push_back( { LK_DIAG_S, d1, ( int64_t )dt.size() - d1, d, 0.0 } );
         /* rows below the diagonal block */
         const int64_t tl0 = ( int64_t )ttl.size(); std::vector<Tile> tbt;
         double tflops = 0;
@@ -756,6 +763,7 @@ static int run_factor( b200_ctx* c ) {
         if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
         else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
+      case LK_DIAG_S: potrf_diag_small_kernel<<<( unsigned )l.count, 256, POTRF_S_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr ); break;
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
       case LK_TRSM_MMA:
         gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
@@ -1144,4 +1152,33 @@ extern "C" double b200_bench_stream_gbs( b200_ctx_t* c, size_t bytes, int iters 
   }
   cudaFree( a ); cudaFree( b );
   return 2.0 * bytes / ( best * 1e-3 ) / 1e9;
+}
+
+/* micro-benchmark of the diagonal-block kernels: which = 0 unrolled register kernel, 1 rolled shared-memory kernel;
+ * ntasks blocks of order nb per launch; returns microseconds per launch (best of iters) */
+extern "C" double b200_bench_potrf_us( b200_ctx_t* c, int which, int nb, int ntasks, int iters ) {
+  if ( !c || nb < 1 || nb > NB || ntasks < 1 ) return -1.0;
+  cudaSetDevice( c->device );
+  const size_t blk = ( size_t )NB * NB;
+  std::vector<double> h( blk * ntasks, 0.0 );
+  for ( int t = 0; t < ntasks; t++ ) for ( int cc = 0; cc < nb; cc++ ) for ( int r = cc; r < nb; r++ ) h[t * blk + r + ( size_t )cc * NB] = r == cc ? 12.0 + 0.01 * ( t % 7 ) : -1.0 / ( 1 + r - cc );
+  double *A0, *A, *inv; int* err; DiagTask* dtk;
+  if ( cudaMalloc( &A0, h.size() * 8 ) || cudaMalloc( &A, h.size() * 8 ) || cudaMalloc( &inv, h.size() * 8 ) || cudaMalloc( &err, 4 ) || cudaMalloc( &dtk, sizeof( DiagTask ) * ntasks ) ) return -1.0;
+  cudaMemcpy( A0, h.data(), h.size() * 8, cudaMemcpyHostToDevice ); cudaMemset( err, 0, 4 );
+  std::vector<DiagTask> tk( ntasks );
+  for ( int t = 0; t < ntasks; t++ ) { tk[t].A = A + t * blk; tk[t].AU = nullptr; tk[t].lda = NB; tk[t].nb = nb; tk[t].inv = inv + t * blk; tk[t].inv2 = nullptr; tk[t].piv = nullptr; tk[t].col = 0; }
+  cudaMemcpy( dtk, tk.data(), sizeof( DiagTask ) * ntasks, cudaMemcpyHostToDevice );
+  float best = 1e30f;
+  for ( int it = 0; it < iters + 2; it++ ) {
+    cudaMemcpyAsync( A, A0, h.size() * 8, cudaMemcpyDeviceToDevice, c->stream );
+    cudaEventRecord( c->ev0, c->stream );
+    if ( which == 0 ) potrf_diag_kernel<<<ntasks, POTRF_THREADS, 0, c->stream>>>( dtk, err );
+    else potrf_diag_small_kernel<<<ntasks, 256, POTRF_S_SMEM, c->stream>>>( dtk, err );
+    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
+    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
+  }
+  int e = 0; cudaMemcpy( &e, err, 4, cudaMemcpyDeviceToHost );
+  cudaFree( A0 ); cudaFree( A ); cudaFree( inv ); cudaFree( err ); cudaFree( dtk );
+  if ( cudaGetLastError() != cudaSuccess || e != 0 ) return -2.0;
+  return best * 1e3;
 }
