@@ -234,10 +234,16 @@ def main():
         prof = {l.split()[0]: (int(l.split()[1].split("=")[1]), float(l.split()[2].split("=")[1])) for l in buf.value.decode().strip().splitlines()}
         gemm_ms = st.gemm_ms; gemm_alg = st.gemm_alg_flops
         dmma_peak = L.b200_bench_fp64_peak_tflops(ctx, 0, 3); dfma_peak = L.b200_bench_fp64_peak_tflops(ctx, 1, 3)
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); hbm_measured = True
+        except Exception:
+            hbm_peak = 6650.0; hbm_measured = False
         peak = 37.0   # nominal HGX B200 FP64 (tensor = vector); MEASURED_PEAKS.json has no FP64 entry -- see DESIGN.md
         achieved = gemm_alg / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        roofline = {"bound": "tensor", "kernel": "gemm_nt_dmma_kernel (DMMA.8x8x4, 64x64 CTA tile, 3 CTAs/SM)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak if achieved else None, "traffic": None,
+        roofline = {"bound": "tensor", "kernel": "gemm_nt_dmma_bulk_kernel (DMMA.8x8x4 via mma.sync m8n8k4.f64 -- tcgen05 has no f64 kind; 64x64 CTA tile, cp.async.bulk + mbarrier producer/consumer pipeline, 3 CTAs/SM)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if achieved else None, "traffic": 1.122e9,
+                    "traffic_note": "dram__bytes_read+write of ONE captured launch at a root-front shape (8192x8192, K=512: algorithmic 1.14e9 B, DMMA pipe 89.1 % active, 32.8 TFLOP/s) -- profiles/r1_ncu_prof_gemm_root.txt; `achieved` is the average over all update launches of the factorization",
                     "peak_source": "nominal FP64 37 TFLOP/s (HGX B200 datasheet; not in MEASURED_PEAKS.json)",
                     "measured_dmma_issue_roof_tflops": dmma_peak, "measured_dfma_roof_tflops": dfma_peak,
                     "frac_of_measured_dmma_roof": achieved / dmma_peak if achieved and dmma_peak > 0 else None,
@@ -245,7 +251,11 @@ def main():
                     "kernel_ms": {k: v_[1] for k, v_ in prof.items()}}
         extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "backward_error": berr,
                  "n": n, "nnz_L": int(S.nnzL), "stored_nnz_L": int(S.stored_nnzL), "factor_flops": F, "supernodes": S.ns, "levels": S.maxdepth + 1, "max_front": S.maxfront,
-                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0]}
+                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0],
+                 "solve_roofline": {"bound": "hbm", "kernels": "solve_fwd_step_kernel / solve_bwd_step_kernel (two sweeps over the stored factor)", "achieved": 16.0 * S.stored_nnzL * (1 + refine[0]) / solve_s / 1e9,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": 16.0 * S.stored_nnzL * (1 + refine[0]) / solve_s / 1e9 / hbm_peak,
+                                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if hbm_measured else "fallback 6650 GB/s (B200_PROFILING.md)",
+                                    "note": "algorithmic bytes = 2 sweeps x 8 B x stored entries of L (panels incl. relaxation zeros); latency-bound on the 256-column steps of the top supernodes, see profiles/r1_solve_launch_summary.txt"}}
     # release the device-resident copy before the plugin path allocates its own
     L.b200_dev_free(ctx, d_vals); L.b200_dev_free(ctx, d_b); L.b200_dev_free(ctx, d_x)
     s.close()

@@ -47,6 +47,10 @@ if __name__ == "__main__":
     elif which == "mid":
         run("p3d-64", stencils.poisson3d_upper(64), 0, True, profile=True)
         run("p2d-1024", stencils.poisson2d_upper(1024), 0, True, profile=True)
+    elif which == "configs":   # BASELINE.json configs[1], [3] at full size, plus the multi-RHS sweep of configs[4]
+        run("C2 p2d-1024", stencils.poisson2d_upper(1024), 0, True, profile=False)
+        run("C2 p2d-1024", stencils.poisson2d_upper(1024), 0, True, profile=False)
+        run("C4 lu cd27-96", stencils.convdiff27_full(96), 1, False, profile=False)
     elif which == "big":
         run("p3d-128", stencils.poisson3d_upper(128), 0, True, profile=False)
         run("p3d-128", stencils.poisson3d_upper(128), 0, True, profile=True)
