@@ -230,8 +230,8 @@ def main():
     L.b200_factor_device(ctx, d_vals); L.b200_get_stats(ctx, C.byref(st))
     L.b200_set_profile(ctx, 0)
     if rank == 0:
-        buf = C.create_string_buffer(4096); L.b200_get_profile(ctx, buf, 4096)
-        prof = {l.split()[0]: (int(l.split()[1].split("=")[1]), float(l.split()[2].split("=")[1])) for l in buf.value.decode().strip().splitlines()}
+        buf = C.create_string_buffer(16384); L.b200_get_profile(ctx, buf, 16384)
+        prof = {l.split()[0]: (int(l.split()[1].split("=")[1]), float(l.split()[2].split("=")[1])) for l in buf.value.decode().strip().splitlines() if " launches=" in l}
         gemm_ms = st.gemm_ms; gemm_alg = st.gemm_alg_flops
         dmma_peak = L.b200_bench_fp64_peak_tflops(ctx, 0, 3); dfma_peak = L.b200_bench_fp64_peak_tflops(ctx, 1, 3)
         try:
@@ -249,9 +249,15 @@ def main():
                     "frac_of_measured_dmma_roof": achieved / dmma_peak if achieved and dmma_peak > 0 else None,
                     "gemm_ms_per_factor": gemm_ms, "gemm_launches": int(st.gemm_launches), "gemm_share_of_factor": gemm_ms / sum(x[1] for x in prof.values()) if prof else None,
                     "kernel_ms": {k: v_[1] for k, v_ in prof.items()}}
+        ns_ = S.ns
+        k_ = np.diff(m.sym_array(s.S, "sn_start", ns_ + 1, np.int32)).astype(np.float64); f_ = np.diff(m.sym_array(s.S, "rowptr", ns_ + 1, np.int64)).astype(np.float64)
+        u_ = f_ - k_; ea_bytes = float(16.0 * (u_ * (u_ + 1) / 2).sum())
         extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "backward_error": berr,
                  "n": n, "nnz_L": int(S.nnzL), "stored_nnz_L": int(S.stored_nnzL), "factor_flops": F, "supernodes": S.ns, "levels": S.maxdepth + 1, "max_front": S.maxfront,
                  "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0],
+                 "extend_add_roofline": {"bound": "hbm", "kernel": "extend_add_kernel", "achieved": ea_bytes / (prof["extend_add"][1] * 1e-3) / 1e9 if prof.get("extend_add", (0, 0))[1] > 0 else None,
+                                         "peak": hbm_peak, "unit": "GB/s", "frac": ea_bytes / (prof["extend_add"][1] * 1e-3) / 1e9 / hbm_peak if prof.get("extend_add", (0, 0))[1] > 0 else None,
+                                         "note": "algorithmic bytes = 16 B x sum_s u_s(u_s+1)/2 (read the child's entry, write the parent's; the read of the parent entry is not counted); ncu at the root level: DRAM traffic 8.7 GB = read child + read/write parent, 3.2 TB/s (profiles/r1_ncu_prof_extend_add.txt)"},
                  "solve_roofline": {"bound": "hbm", "kernels": "solve_fwd_step_kernel / solve_bwd_step_kernel (two sweeps over the stored factor)", "achieved": 16.0 * S.stored_nnzL * (1 + refine[0]) / solve_s / 1e9,
                                     "peak": hbm_peak, "unit": "GB/s", "frac": 16.0 * S.stored_nnzL * (1 + refine[0]) / solve_s / 1e9 / hbm_peak,
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if hbm_measured else "fallback 6650 GB/s (B200_PROFILING.md)",

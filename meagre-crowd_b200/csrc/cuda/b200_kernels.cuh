@@ -132,13 +132,15 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
       const double* s = src + ( int64_t )j * lduc;
       if ( !LU ) {
         /* lower triangle only: i >= j, hence rel[i] >= dj */
-        if ( dj < kp ) {
-          double* d = Lp + ( int64_t )dj * ldp;
-          for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
-        } else {
-          double* d = CBp + ( int64_t )( dj - kp ) * ldup - kp;
-          for ( int i = j + lane; i < uc; i += 32 ) d[rel[i]] += s[i];
+        double* d = dj < kp ? Lp + ( int64_t )dj * ldp : CBp + ( int64_t )( dj - kp ) * ldup - kp;
+        int i = j + lane;
+        for ( ; i + 96 < uc; i += 128 ) {      /* four independent gather / add / scatter chains per lane in flight */
+          const double s0 = s[i], s1 = s[i + 32], s2 = s[i + 64], s3 = s[i + 96];
+          const int r0 = rel[i], r1 = rel[i + 32], r2 = rel[i + 64], r3 = rel[i + 96];
+          const double d0 = d[r0], d1 = d[r1], d2 = d[r2], d3 = d[r3];
+          d[r0] = d0 + s0; d[r1] = d1 + s1; d[r2] = d2 + s2; d[r3] = d3 + s3;
         }
+        for ( ; i < uc; i += 32 ) d[rel[i]] += s[i];
       } else {
         /* full block: (di,dj) goes to the L panel (di>=dj, dj pivot), the U' panel
          * (di<dj, di pivot; stored transposed) or the parent's contribution block */

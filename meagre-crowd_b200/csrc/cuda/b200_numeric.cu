@@ -397,7 +397,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         bool any = false;
         for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
         if ( !any ) continue;
-        for ( int c0 = 0; c0 < meta[s].f; c0 += ASM_COLS ) if ( owns( s, c0 ) ) at.push_back( { s, c0, std::min( ASM_COLS, meta[s].f - c0 ) } );
+        const int acols = meta[s].f >= 4096 ? ASM_COLS / 2 : ASM_COLS;      /* large fronts: finer tasks, so that the single partial wave of CTAs balances */
+        for ( int c0 = 0; c0 < meta[s].f; c0 += acols ) if ( owns( s, c0 ) ) at.push_back( { s, c0, std::min( acols, meta[s].f - c0 ) } );
       }
       if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
     }

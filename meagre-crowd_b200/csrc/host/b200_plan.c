@@ -28,7 +28,12 @@
 #include <math.h>
 #include "solver_b200.h"
 
-int b200_outer_width( int maxfront ) { return maxfront >= 6144 ? 512 : maxfront >= 1536 ? 256 : 128; }
+int b200_outer_width( int maxfront ) {
+  static int top = -1, top_at = 0;
+  if ( top < 0 ) { const char* e = getenv( "B200_NBO_TOP" ); top = e ? atoi( e ) : 0; const char* a = getenv( "B200_NBO_TOP_AT" ); top_at = a ? atoi( a ) : 16384; }
+  if ( top > 0 && maxfront >= top_at ) return top;
+  return maxfront >= 6144 ? 512 : maxfront >= 1536 ? 256 : 128;
+}
 
 static int cmp_work_desc( const void* a, const void* b, void* ctx ) {
   const double* w = ( const double* )ctx;
