@@ -199,6 +199,7 @@ extern "C" int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id2
   if ( c->comm ) { g_nccl.CommDestroy( c->comm ); c->comm = nullptr; }
   if ( c->comm2 ) { g_nccl.CommDestroy( c->comm2 ); c->comm2 = nullptr; }
   c->rank = rank; c->world = world;
+  { const char* e = getenv( "B200_NBO_CAP" ); b200_set_outer_width_cap( e ? atoi( e ) : ( world >= 4 ? 256 : 0 ) ); }
   if ( world == 1 ) return B200_OK;
   if ( !id256 ) return B200_ERR_ARG;
   if ( load_nccl() ) return B200_ERR_CUDA;
@@ -417,6 +418,26 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
       const size_t panel_first = LS.size();
       int ev_fwd_last = -1;                 /* last per-block panel piece I received as the owner of the next panel */
       for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
+        if ( j0 > J ) { /* left-looking inside the outer panel: the 64 columns about to be factored receive the update of ALL earlier
+                         * blocks of the panel in one product (K = j0 - J) -- one read-modify-write of 64 columns instead of one
+                         * K = 64 pass over the rest of the panel after every block (3.5x less traffic, a K the DMMA pipeline can fill) */
+          const int64_t b0 = ( int64_t )tb.size();
+          double fb = 0;
+          for ( int s : lv ) {
+            const SnMeta& m = meta[s];
+            if ( j0 >= m.k || !owns( s, J ) ) continue;
+            const int nb = std::min( NB, m.k - j0 ); const int kk = j0 - J;
+            double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+            double fl = 0;
+            if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );
+            else {
+              add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Up + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );
+              add_gemm( gt, tb, ts, fl, Up + j0 + ( int64_t )j0 * m.ld, m.ld, Up + j0 + ( int64_t )J * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, -1 );
+            }
+            fb += fl;
+          }
+          if ( ( int64_t )tb.size() > b0 ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, fb } ); }
+        }
         const int64_t d0 = ( int64_t )dt.size(); int64_t d1 = d0;
         for ( int pass = 0; pass < 2; pass++ ) {           /* full 64-column blocks first (unrolled register kernel), then the narrower ones */
           for ( int s : lv ) {
@@ -491,24 +512,6 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           }
         }
         if ( !have_diag ) continue;
-        /* update of the remaining columns of this outer panel */
-        const int64_t b0 = ( int64_t )tb.size();
-        double fb = 0;
-        for ( int s : lv ) {
-          const SnMeta& m = meta[s];
-          if ( j0 >= m.k || !owns( s, J ) ) continue;
-          const int nb = std::min( NB, m.k - j0 ); const int jn = j0 + nb; const int jend = std::min( m.k, J + NBO );
-          if ( jn >= jend ) continue;
-          double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
-          double fl = 0;
-          if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, 0 );
-          else {
-            add_gemm( gt, tb, ts, fl, Lp + jn + ( int64_t )jn * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, Up + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, 0 );
-            add_gemm( gt, tb, ts, fl, Up + jn + ( int64_t )jn * m.ld, m.ld, Up + jn + ( int64_t )j0 * m.ld, m.ld, Lp + jn + ( int64_t )j0 * m.ld, m.ld, m.f - jn, jend - jn, nb, 1, -1 );
-          }
-          fb += fl;
-        }
-        if ( ( int64_t )tb.size() > b0 ) { LS.push_back( { LK_GEMM_BIG, b0, ( int64_t )tb.size() - b0, d, 0.0 } ); LS.back().flops += fb; }
       }
       int ev_panel = -1;
       if ( look ) { /* my compute launches of this panel go to the panel stream */

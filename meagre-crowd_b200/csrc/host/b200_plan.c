@@ -28,11 +28,16 @@
 #include <math.h>
 #include "solver_b200.h"
 
+/* Outer panel width (= K of the trailing update = column-block width of distributed fronts) from a level's largest
+ * front.  On one GPU the factorization is bound by the DMMA update, which likes K = 512; with several GPUs the top
+ * fronts are bound by the chain panel -> transfer -> update of the next panel's columns, whose in-panel and
+ * next-panel parts grow with the SQUARE of the width, so the width is capped (b200_set_outer_width_cap). */
+static int g_width_cap = 0;
+void b200_set_outer_width_cap( int cap ) { g_width_cap = cap; }
 int b200_outer_width( int maxfront ) {
-  static int top = -1, top_at = 0;
-  if ( top < 0 ) { const char* e = getenv( "B200_NBO_TOP" ); top = e ? atoi( e ) : 0; const char* a = getenv( "B200_NBO_TOP_AT" ); top_at = a ? atoi( a ) : 16384; }
-  if ( top > 0 && maxfront >= top_at ) return top;
-  return maxfront >= 6144 ? 512 : maxfront >= 1536 ? 256 : 128;
+  int w = maxfront >= 6144 ? 512 : maxfront >= 1536 ? 256 : 128;
+  if ( g_width_cap > 0 && w > g_width_cap ) w = g_width_cap;
+  return w;
 }
 
 static int cmp_work_desc( const void* a, const void* b, void* ctx ) {
