@@ -160,7 +160,7 @@ typedef struct b200_plan {
 typedef struct b200_xfer { int src, dst, sn; int64_t offset, count; } b200_xfer_t;   /* doubles, inside the child's contribution-block arena */
 
 int b200_outer_width( int maxfront );
-void b200_set_outer_width_cap( int cap );   /* 0 = none; set by b200_mg_init for world >= 4 (see b200_plan.c) */
+void b200_set_outer_width_cap( int cap );   /* 0 = none (default); experiment hook, env B200_NBO_CAP at b200_mg_init */
 b200_plan_t* b200_plan_create( const b200_symbolic_t* S, int world, int min_dist_front );
 void b200_plan_free( b200_plan_t* pl );
 int b200_plan_col_owner( const b200_plan_t* pl, const b200_symbolic_t* S, int s, int c );

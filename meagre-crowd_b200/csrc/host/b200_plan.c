@@ -31,7 +31,8 @@
 /* Outer panel width (= K of the trailing update = column-block width of distributed fronts) from a level's largest
  * front.  On one GPU the factorization is bound by the DMMA update, which likes K = 512; with several GPUs the top
  * fronts are bound by the chain panel -> transfer -> update of the next panel's columns, whose in-panel and
- * next-panel parts grow with the SQUARE of the width, so the width is capped (b200_set_outer_width_cap). */
+ * next-panel parts grow with the SQUARE of the width; a cap can be set (b200_set_outer_width_cap, env B200_NBO_CAP),
+ * but measured at 4 GPUs it does not pay (256: 273 ms, 512: 266 ms) -- per-block costs dominate the chain. */
 static int g_width_cap = 0;
 void b200_set_outer_width_cap( int cap ) { g_width_cap = cap; }
 int b200_outer_width( int maxfront ) {
