@@ -216,6 +216,10 @@ def main():
         factor_s, solve_s, wall = t.tolist()
         tl = torch.tensor([launches], device="cuda", dtype=torch.int64); dist.all_reduce(tl); launches = int(tl.item())
     value = F / factor_s / 1e9     # one factorization shared by all ranks (strong scaling)
+    L.b200_get_stats(ctx, C.byref(st)); nvlink_bytes = float(st.comm_bytes)
+    if dist is not None:
+        import torch
+        tb_ = torch.tensor([nvlink_bytes], device="cuda", dtype=torch.float64); dist.all_reduce(tb_); nvlink_bytes = tb_.item() / 2.0   # every message is counted by its sender and its receiver
 
     # correctness gate on the timed configuration: scaled backward error <= 1e-12
     x = np.empty(n); L.b200_dev_download(ctx, x.ctypes.data, d_x, x.nbytes)
@@ -254,7 +258,7 @@ def main():
         u_ = f_ - k_; ea_bytes = float(16.0 * (u_ * (u_ + 1) / 2).sum())
         extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "backward_error": berr,
                  "n": n, "nnz_L": int(S.nnzL), "stored_nnz_L": int(S.stored_nnzL), "factor_flops": F, "supernodes": S.ns, "levels": S.maxdepth + 1, "max_front": S.maxfront,
-                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0],
+                 "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0], "nccl_bytes_per_factor": nvlink_bytes,
                  "extend_add_roofline": {"bound": "hbm", "kernel": "extend_add_kernel", "achieved": ea_bytes / (prof["extend_add"][1] * 1e-3) / 1e9 if prof.get("extend_add", (0, 0))[1] > 0 else None,
                                          "peak": hbm_peak, "unit": "GB/s", "frac": ea_bytes / (prof["extend_add"][1] * 1e-3) / 1e9 / hbm_peak if prof.get("extend_add", (0, 0))[1] > 0 else None,
                                          "note": "algorithmic bytes = 16 B x sum_s u_s(u_s+1)/2 (read the child's entry, write the parent's; the read of the parent entry is not counted); ncu at the root level: DRAM traffic 8.7 GB = read child + read/write parent, 3.2 TB/s (profiles/r1_ncu_prof_extend_add.txt)"},

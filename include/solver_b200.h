@@ -198,6 +198,7 @@ typedef struct b200_stats {
   int refine_steps;        /* refinement steps taken by the last solve       */
   double backward_error;   /* componentwise backward error seen before the last decision (automatic mode), else -1 */
   double first_backward_error;  /* the same quantity for the unrefined solution (automatic mode), else -1 */
+  double comm_bytes;       /* multi-GPU: bytes this rank sends + receives over NCCL per factorization (0 on one GPU) */
 } b200_stats_t;
 int b200_get_stats( b200_ctx_t* c, b200_stats_t* out );
 /* per-kernel timing of the next factor (serialises launches; diagnostics only) */

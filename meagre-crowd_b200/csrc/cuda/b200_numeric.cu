@@ -815,7 +815,7 @@ static int run_factor( b200_ctx* c ) {
   c->stats.factor_ms = ms; c->stats.launches = nlaunch; c->stats.gemm_flops = gemm_flops; c->stats.gemm_launches = gemm_launches;
   c->stats.gemm_alg_flops = c->gemm_alg_flops * ( c->flops_stored > 0 ? c->flops_exact / c->flops_stored : 1.0 );
   c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] : 0.0;
-  c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes;
+  c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes; c->stats.comm_bytes = c->comm_bytes;
   if ( err != 0 ) { char a[64]; snprintf( a, 64, "%d", err - 1 ); set_err( "matrix is not positive definite (pivot column %s of the permuted matrix)%s", a, "" ); c->factored = false; return B200_ERR_NOT_SPD; }
   c->factored = true;
   return B200_OK;

@@ -165,6 +165,32 @@ def test_solve_is_linear(mc):
     s.close()
 
 
+@pytest.mark.parametrize("kind", ["cholesky", "lu"])
+def test_sweeps_over_several_256_column_blocks_and_rhs_chunks(mc, kind):
+    """root supernode wider than one 256-column solve block (look-ahead finish by chunk partials, both sweeps), 19 right-hand
+    sides = three chunks of eight: every column must be bit-identical to the one-column solve and agree with SuperLU"""
+    import scipy.sparse.linalg as sla
+    if kind == "cholesky":
+        n, cp, ri, v = stencils.poisson3d_upper(30); A = stencils.to_scipy(n, cp, ri, v, True); k = mc.KIND_CHOLESKY
+    else:
+        n, cp, ri, v = stencils.convdiff27_full(22); A = stencils.to_scipy(n, cp, ri, v, False); k = mc.KIND_LU
+    s = mc.Solver(); S = s.analyze(n, cp, ri, k)
+    st = mc.sym_array(s.S, "sn_start", S.ns + 1, np.int32)
+    assert np.diff(st).max() > 2 * 256, "the case must have a supernode spanning several solve blocks"
+    s.L.b200_set_refinement(s.ctx, 0)
+    assert s.factor(v) == 0
+    rng = np.random.default_rng(7); B = rng.standard_normal((n, 19))
+    X = s.solve(B)
+    for c in (0, 7, 8, 18):
+        assert np.array_equal(X[:, c], s.solve(B[:, c].copy()))
+    lu = sla.splu(A.tocsc())
+    Xr = lu.solve(B)
+    assert np.abs(X - Xr).max() <= 1e-10 * np.abs(Xr).max()
+    for c in range(19):
+        assert backward_error(A, X[:, c], B[:, c]) <= 1e-12
+    s.close()
+
+
 def test_not_positive_definite_is_reported_not_hidden(mc, golden):
     Ad = read_mm_dense(f"{golden}/sym.mm")
     U = sp.triu(sp.csc_matrix(Ad)).tocsc(); U.sort_indices()
