@@ -134,11 +134,14 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
         /* lower triangle only: i >= j, hence rel[i] >= dj */
         double* d = dj < kp ? Lp + ( int64_t )dj * ldp : CBp + ( int64_t )( dj - kp ) * ldup - kp;
         int i = j + lane;
-        for ( ; i + 96 < uc; i += 128 ) {      /* four independent gather / add / scatter chains per lane in flight */
-          const double s0 = s[i], s1 = s[i + 32], s2 = s[i + 64], s3 = s[i + 96];
-          const int r0 = rel[i], r1 = rel[i + 32], r2 = rel[i + 64], r3 = rel[i + 96];
-          const double d0 = d[r0], d1 = d[r1], d2 = d[r2], d3 = d[r3];
-          d[r0] = d0 + s0; d[r1] = d1 + s1; d[r2] = d2 + s2; d[r3] = d3 + s3;
+        for ( ; i + 224 < uc; i += 256 ) {     /* eight independent gather / add / scatter chains per lane in flight */
+          double sv[8], dv[8]; int rv[8];
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) { sv[q] = s[i + 32 * q]; rv[q] = rel[i + 32 * q]; }
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) dv[q] = d[rv[q]];
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) d[rv[q]] = dv[q] + sv[q];
         }
         for ( ; i < uc; i += 32 ) d[rel[i]] += s[i];
       } else {
