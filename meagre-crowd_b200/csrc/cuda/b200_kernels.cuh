@@ -676,6 +676,115 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt
   }
 }
 
+/* ------------------------------------------- DMMA GEMM NT, persistent CTAs
+ * The bulk-copy kernel above pays the fill of its 4-stage pipeline once per 64x64 tile; with K = 128..256 (mid tree
+ * levels, in-panel updates) that bubble is a large share of the tile (21 TFLOP/s at K = 128 against 33 at K = 512).
+ * Here a CTA walks over tiles ti = blockIdx.x, blockIdx.x + gridDim.x, ...: the producer warp never stops at a tile
+ * boundary -- while the consumer warps write back tile i it is already filling the stages with tile i+1 -- and the
+ * mbarrier phases simply keep counting k-steps across tiles.  Same shared-memory layout, same arithmetic order. */
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt_dmma_pers_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles, int ntiles,
+                                                                                               const double* __restrict__ zeros ) {
+  constexpr int BK = 16;
+  constexpr int NCW = ( BM / WM ) * ( BN / WN );
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  extern __shared__ double sm[];
+  double* As = sm;
+  double* Bs = sm + STAGES * BK * LDA;
+  uint64_t* full = reinterpret_cast<uint64_t*>( sm + STAGES * BK * ( LDA + LDB ) );
+  uint64_t* empty = full + STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ( tid == 0 ) {
+    for ( int s = 0; s < STAGES; s++ ) { mbar_init( &full[s], 1 ); mbar_init( &empty[s], NCW ); }
+    asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
+    asm volatile( "fence.proxy.async.shared::cta;\n" ::: "memory" );
+  }
+  __syncthreads();
+  unsigned g = 0;                                   /* k-steps issued / consumed so far by this CTA, over all its tiles */
+  if ( warp == NCW ) {
+    /* ---------------- producer warp */
+    const int q = lane & 15; const bool isb = lane >= 16;
+    for ( int ti = blockIdx.x; ti < ntiles; ti += gridDim.x ) {
+      const Tile tl = tiles[ti];
+      const GemmTask t = tasks[tl.task];
+      const int m0 = tl.tm * BM, n0 = tl.tn * BN;
+      const int mrem = t.M - m0, nrem = t.N - n0;
+      const double* Ag = t.A + m0;
+      const double* Bg = t.B + n0;
+      const int sa = ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ), sb = ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 );
+      const int K = t.K, nk = ( K + BK - 1 ) / BK;
+      const int ra = ( ( min( BM, mrem ) + sa + 1 ) & ~1 ) * 8, rb = ( ( min( BN, nrem ) + sb + 1 ) & ~1 ) * 8;
+      const double* gsrc = isb ? Bg - sb : Ag - sa;
+      const int64_t ldg = isb ? t.ldb : t.lda;
+      const int bytes = isb ? rb : ra;
+      for ( int kt = 0; kt < nk; kt++, g++ ) {
+        const unsigned slot = g % STAGES, use = g / STAGES;
+        if ( lane == 0 ) {
+          if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 );
+          mbar_expect_tx( &full[slot], BK * ( ra + rb ) );
+        }
+        __syncwarp();
+        double* dst = isb ? Bs + slot * BK * LDB + q * LDB : As + slot * BK * LDA + q * LDA;
+        const int kq = kt * BK + q;
+        bulk_g2s( dst, kq < K ? ( const void* )( gsrc + ( int64_t )kq * ldg ) : ( const void* )zeros, bytes, &full[slot] );
+      }
+    }
+    return;
+  }
+  /* ---------------- consumers */
+  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
+  const int fr = lane >> 2, fk = lane & 3;
+  for ( int ti = blockIdx.x; ti < ntiles; ti += gridDim.x ) {
+    const Tile tl = tiles[ti];
+    const GemmTask t = tasks[tl.task];
+    const int m0 = tl.tm * BM, n0 = tl.tn * BN;
+    const int sa = ( int )( ( ( uintptr_t )( t.A + m0 ) >> 3 ) & 1 ), sb = ( int )( ( ( uintptr_t )( t.B + n0 ) >> 3 ) & 1 );
+    const int nk = ( t.K + BK - 1 ) / BK;
+    double acc[MT][NTL][2];
+#pragma unroll
+    for ( int i = 0; i < MT; i++ )
+#pragma unroll
+      for ( int j = 0; j < NTL; j++ ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for ( int kt = 0; kt < nk; kt++, g++ ) {
+      const unsigned slot = g % STAGES;
+      mbar_wait( &full[slot], ( g / STAGES ) & 1 );
+      const double* as = As + slot * BK * LDA + wm0 + fr + sa;
+      const double* bs = Bs + slot * BK * LDB + wn0 + fr + sb;
+#pragma unroll
+      for ( int kk = 0; kk < BK; kk += 4 ) {
+        double af[MT], bf[NTL];
+#pragma unroll
+        for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
+#pragma unroll
+        for ( int j = 0; j < NTL; j++ ) bf[j] = bs[( kk + fk ) * LDB + j * 8];
+#pragma unroll
+        for ( int i = 0; i < MT; i++ )
+#pragma unroll
+          for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
+      }
+      __syncwarp();
+      if ( lane == 0 ) mbar_arrive( &empty[slot] );
+    }
+    double* Cg = t.C;
+#pragma unroll
+    for ( int j = 0; j < NTL; j++ ) {
+#pragma unroll
+      for ( int h = 0; h < 2; h++ ) {
+        const int c = n0 + wn0 + j * 8 + 2 * fk + h;
+        if ( c < t.N ) {
+          double* cc = Cg + ( int64_t )c * t.ldc;
+#pragma unroll
+          for ( int i = 0; i < MT; i++ ) {
+            const int r = m0 + wm0 + i * 8 + fr;
+            if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
+          }
+        }
+      }
+    }
+  }
+}
+
 /* -------------------------------------------------------------- solves */
 constexpr int PC = 8;   /* right-hand sides per pass */
 

@@ -125,7 +125,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true, use_pers = true; int pers_grid = 444;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -173,6 +173,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
+  CKN( cudaFuncSetAttribute( gemm_nt_dmma_pers_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
+  c->use_pers = getenv( "B200_GEMM_NO_PERSISTENT" ) == nullptr; c->pers_grid = c->prop.multiProcessorCount * 3;
   CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
   c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
@@ -770,10 +772,12 @@ static int run_factor( b200_ctx* c ) {
       case LK_DIAG_S: potrf_diag_small_kernel<<<( unsigned )l.count, 256, POTRF_S_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr ); break;
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
       case LK_TRSM_MMA:
-        gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
+        if ( c->use_pers ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<int64_t>( l.count, c->pers_grid ), BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, ( int )l.count, c->dZeros );
+        else gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
         break;
       case LK_GEMM_BIG:
-        if ( c->use_bulk ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
+        if ( c->use_bulk && c->use_pers ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<int64_t>( l.count, c->pers_grid ), BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, ( int )l.count, c->dZeros );
+        else if ( c->use_bulk ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
         else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
         gemm_flops += l.flops; gemm_launches++; break;
       case LK_NOP: break;
@@ -1036,7 +1040,8 @@ extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, i
   for ( int it = 0; it < iters + 2; it++ ) {
     cudaEventRecord( c->ev0, c->stream );
     if ( dtb.n ) {
-      if ( c->use_bulk && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )dtb.n, BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, c->dZeros );
+      if ( c->use_bulk && c->use_pers && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<size_t>( dtb.n, c->pers_grid ), BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, ( int )dtb.n, c->dZeros );
+      else if ( c->use_bulk && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )dtb.n, BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, c->dZeros );
       else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )dtb.n, GEMM_THREADS, BIG_SMEM, c->stream>>>( dgt.d, dtb.d );
     }
     cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
@@ -1185,4 +1190,46 @@ extern "C" double b200_bench_potrf_us( b200_ctx_t* c, int which, int nb, int nta
   cudaFree( A0 ); cudaFree( A ); cudaFree( inv ); cudaFree( err ); cudaFree( dtk );
   if ( cudaGetLastError() != cudaSuccess || e != 0 ) return -2.0;
   return best * 1e3;
+}
+
+/* tuning aid: the bulk-copy DMMA kernel with other tile configurations (C -= A B', plain rectangular task) */
+template <int BM, int BN, int WM, int WN, int ST>
+static double bench_bulk_variant( b200_ctx* c, int m, int n, int k, int iters ) {
+  constexpr int SMEM = ST * 16 * ( BM + 4 + BN + 4 ) * 8 + 2 * ST * 8;
+  constexpr int NT = ( BM / WM ) * ( BN / WN ) * 32 + 32;
+  if ( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<BM, BN, WM, WN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM ) != cudaSuccess ) { cudaGetLastError(); return -1.0; }
+  double *A, *B, *C;
+  if ( cudaMalloc( &A, ( size_t )m * k * 8 ) || cudaMalloc( &B, ( size_t )n * k * 8 ) || cudaMalloc( &C, ( size_t )m * n * 8 ) ) return -1.0;
+  cudaMemset( A, 0, ( size_t )m * k * 8 ); cudaMemset( B, 0, ( size_t )n * k * 8 ); cudaMemset( C, 0, ( size_t )m * n * 8 );
+  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = m; t.lda = m; t.ldb = n; t.M = m; t.N = n; t.K = k; t.lower = 0; t.diag = 0; t.mode = 0;
+  std::vector<GemmTask> gt( 1, t ); std::vector<Tile> tl;
+  for ( int tn = 0; tn * BN < n; tn++ ) for ( int tm = 0; tm * BM < m; tm++ ) { Tile x; x.task = 0; x.tm = ( unsigned short )tm; x.tn = ( unsigned short )tn; tl.push_back( x ); }
+  DevVec<GemmTask> dgt; DevVec<Tile> dtl; dgt.upload( gt ); dtl.upload( tl );
+  float best = 1e30f;
+  for ( int it = 0; it < iters + 2; it++ ) {
+    cudaEventRecord( c->ev0, c->stream );
+    gemm_nt_dmma_bulk_kernel<BM, BN, WM, WN, ST><<<( unsigned )dtl.n, NT, SMEM, c->stream>>>( dgt.d, dtl.d, c->dZeros );
+    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
+    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  dgt.release(); dtl.release(); cudaFree( A ); cudaFree( B ); cudaFree( C );
+  if ( e != cudaSuccess ) { set_err( "bulk variant: %s", cudaGetErrorString( e ) ); return -1.0; }
+  return 2.0 * m * n * ( double )k / ( best * 1e-3 ) / 1e12;
+}
+extern "C" double b200_bench_dgemm_bulk_variant( b200_ctx_t* c, int variant, int m, int n, int k, int iters ) {
+  if ( !c ) return -1.0;
+  cudaSetDevice( c->device );
+  switch ( variant ) {
+    case 0: return bench_bulk_variant<64, 64, 32, 16, 4>( c, m, n, k, iters );      /* production */
+    case 1: return bench_bulk_variant<128, 64, 32, 32, 4>( c, m, n, k, iters );
+    case 2: return bench_bulk_variant<64, 128, 32, 32, 4>( c, m, n, k, iters );
+    case 3: return bench_bulk_variant<128, 64, 64, 16, 4>( c, m, n, k, iters );
+    case 4: return bench_bulk_variant<64, 64, 32, 16, 6>( c, m, n, k, iters );
+    case 5: return bench_bulk_variant<64, 64, 16, 32, 4>( c, m, n, k, iters );
+    case 6: return bench_bulk_variant<128, 64, 32, 32, 3>( c, m, n, k, iters );
+    case 7: return bench_bulk_variant<128, 128, 64, 32, 3>( c, m, n, k, iters );
+    case 8: return bench_bulk_variant<64, 64, 32, 32, 4>( c, m, n, k, iters );
+    default: return -1.0;
+  }
 }
