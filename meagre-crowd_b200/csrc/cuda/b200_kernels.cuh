@@ -681,7 +681,10 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt
  * levels, in-panel updates) that bubble is a large share of the tile (21 TFLOP/s at K = 128 against 33 at K = 512).
  * Here a CTA walks over tiles ti = blockIdx.x, blockIdx.x + gridDim.x, ...: the producer warp never stops at a tile
  * boundary -- while the consumer warps write back tile i it is already filling the stages with tile i+1 -- and the
- * mbarrier phases simply keep counting k-steps across tiles.  Same shared-memory layout, same arithmetic order. */
+ * mbarrier phases simply keep counting k-steps across tiles.  Same shared-memory layout, same arithmetic order.
+ * EXPERIMENTAL (env B200_GEMM_PERSISTENT=1): with a static round-robin tile assignment it measured 22.1 / 18.8 TFLOP/s
+ * at K = 128 / 64 (one-tile kernel: 21.1 / 15.0) but only 28.3 at K = 512 (32.9), and a slower 128^3 factorization
+ * (752 vs 673 ms), so the one-tile-per-CTA kernel stays the production path. */
 template <int BM, int BN, int WM, int WN, int STAGES>
 __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt_dmma_pers_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles, int ntiles,
                                                                                                const double* __restrict__ zeros ) {
