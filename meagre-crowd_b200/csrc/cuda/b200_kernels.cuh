@@ -288,6 +288,94 @@ __global__ void __launch_bounds__( 256 ) potrf_diag_small_kernel( const DiagTask
   }
 }
 
+/* ---------------------------------------------------- small fronts, one CTA per front
+ * The deep tree levels hold ~90 % of the supernodes and ~0.04 % of the flops (128^3: 119 330 fronts with k <= 32
+ * pivots and f <= 160 rows).  Driving them through the four generic launches of a level (diagonal block, row update,
+ * in-panel update, trailing update on 64x64 tensor tiles that are almost all padding) costs a few milliseconds per
+ * level.  Here one CTA takes a whole front: the f x k panel goes to shared memory, is eliminated column by column
+ * (right-looking over ALL rows, so the row update needs no inverse; one barrier per column), the top block is inverted
+ * for the sweeps, and the contribution block receives  -L21 L21'  in 4x4 register blocks.  Cholesky only. */
+constexpr int SF_KMAX = 32, SF_FMAX = 160, SF_LD = SF_KMAX + 1;
+constexpr int SF_SMEM = ( ( SF_FMAX + 4 ) * SF_LD + SF_KMAX * SF_LD + SF_KMAX ) * 8;
+__global__ void __launch_bounds__( 256 ) small_front_kernel( const int* __restrict__ sns, const SnMeta* __restrict__ sn, double* __restrict__ L, double* __restrict__ inv,
+                                                             double* __restrict__ CB, int* __restrict__ err ) {
+  extern __shared__ double dsm[];
+  double ( *P )[SF_LD] = reinterpret_cast<double ( * )[SF_LD]>( dsm );                                    /* [f][k] */
+  double ( *X )[SF_LD] = reinterpret_cast<double ( * )[SF_LD]>( dsm + ( SF_FMAX + 4 ) * SF_LD );          /* [k][k] */
+  double* rsv = dsm + ( SF_FMAX + 4 ) * SF_LD + SF_KMAX * SF_LD;
+  const SnMeta S = sn[sns[blockIdx.x]];
+  const int k = S.k, f = S.f, u = f - k, tid = threadIdx.x;
+  double* Lp = L + S.lptr;
+  for ( int e = tid; e < f * k; e += 256 ) { const int r = e % f, c = e / f; P[r][c] = ( r >= c ) ? Lp[r + ( int64_t )c * S.ld] : 0.0; }
+  for ( int e = tid; e < 4 * k; e += 256 ) P[f + e / k][e % k] = 0.0;          /* rows read by the last 4x4 blocks of the update */
+  for ( int e = tid; e < k * k; e += 256 ) X[e / k][e % k] = 0.0;
+  __syncthreads();
+  for ( int j = 0; j < k; j++ ) {
+    double d = P[j][j];
+    if ( !( d > 0.0 ) ) { if ( tid == 0 ) atomicCAS( err, 0, S.c0 + j + 1 ); d = 1.0; }
+    const double rs = rsqrt( d );
+    if ( tid == 0 ) rsv[j] = rs;
+    const double rs2 = rs * rs;
+    const int nrow = f - 1 - j, ncol = k - 1 - j;
+    for ( int e = tid; e < nrow * ncol; e += 256 ) {          /* column j stays unscaled in place: l(r,j) l(c,j) = a(r,j) a(c,j) / d */
+      const int r = j + 1 + e % nrow, c = j + 1 + e / nrow;
+      if ( r >= c ) P[r][c] -= P[r][j] * rs2 * P[c][j];
+    }
+    __syncthreads();
+  }
+  for ( int e = tid; e < f * k; e += 256 ) {
+    const int r = e % f, c = e / f;
+    if ( r >= c ) { const double l = P[r][c] * rsv[c]; P[r][c] = l; Lp[r + ( int64_t )c * S.ld] = l; }
+  }
+  __syncthreads();
+  { /* inverse of the top block, four lanes per column */
+    const int col = tid >> 2, part = tid & 3;
+    if ( col < k && part == 0 ) X[col][col] = rsv[col];
+    __syncwarp();
+    for ( int i = 1; i < k; i++ ) {
+      double sacc = 0.0;
+      if ( col < k && i > col ) for ( int q = col + part; q < i; q += 4 ) sacc += P[i][q] * X[q][col];
+      sacc += __shfl_xor_sync( 0xffffffffu, sacc, 1 );
+      sacc += __shfl_xor_sync( 0xffffffffu, sacc, 2 );
+      if ( col < k && i > col && part == 0 ) X[i][col] = -sacc * rsv[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  { double* ip = inv + S.invptr; for ( int e = tid; e < k * k; e += 256 ) { const int r = e % k, c = e / k; ip[r + c * k] = X[r][c]; } }
+  if ( u == 0 ) return;
+  /* contribution block (lower triangle): C(i,j) -= sum_c L21(i,c) L21(j,c) */
+  double* cbp = CB + S.cbptr;
+  const int64_t ldu = ( u + 1 ) & ~1;
+  const int nb4 = ( u + 3 ) >> 2;
+  for ( int b = tid; b < nb4 * nb4; b += 256 ) {
+    const int bi = b % nb4, bj = b / nb4;
+    if ( bi < bj ) continue;
+    double acc[4][4];
+#pragma unroll
+    for ( int x = 0; x < 4; x++ )
+#pragma unroll
+      for ( int y = 0; y < 4; y++ ) acc[x][y] = 0.0;
+    const int ri = k + 4 * bi, rj = k + 4 * bj;
+    for ( int c = 0; c < k; c++ ) {
+      double av[4], bv[4];
+#pragma unroll
+      for ( int x = 0; x < 4; x++ ) { av[x] = P[ri + x][c]; bv[x] = P[rj + x][c]; }
+#pragma unroll
+      for ( int x = 0; x < 4; x++ )
+#pragma unroll
+        for ( int y = 0; y < 4; y++ ) acc[x][y] += av[x] * bv[y];
+    }
+#pragma unroll
+    for ( int y = 0; y < 4; y++ )
+#pragma unroll
+      for ( int x = 0; x < 4; x++ ) {
+        const int i = 4 * bi + x, jj = 4 * bj + y;
+        if ( i < u && jj < u && i >= jj ) cbp[i + ( int64_t )jj * ldu] -= acc[x][y];
+      }
+  }
+}
+
 /* ------------------------------------------------------ diagonal block: LU
  * LU of an nb x nb block with partial pivoting restricted to the block's own
  * rows.  piv[j] = block-local row swapped into position j.  Tiny pivots are

@@ -82,8 +82,8 @@ constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 
-enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_DIAG_S, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
-static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "diag_block_small", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
+enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_DIAG_S, LK_SMALL_FRONT, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
+static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "diag_block_small", "small_front", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
 /* one point-to-point message of the multi-GPU schedule: which = 0 L storage, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
 struct Msg { int src, dst, which; int64_t off, cnt; };
 
@@ -125,7 +125,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true, use_pers = false; int pers_grid = 444;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true, use_pers = false, use_small_front = true; DevVec<int> small_sns; int pers_grid = 444;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -179,6 +179,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
+  CKN( cudaFuncSetAttribute( small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM ) );
+  c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
   memset( &c->stats, 0, sizeof( c->stats ) );
@@ -219,7 +221,7 @@ static void release_symbolic( b200_ctx* c ) {
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
   c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
   c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
-  c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release(); c->gather_tasks.release();
+  c->small_sns.release(); c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release(); c->gather_tasks.release();
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart );
   c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->dPart = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
@@ -339,6 +341,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   std::vector<GemmTask> gt; std::vector<Tile> tb, ts; std::vector<DiagTask> dt; std::vector<TrsmTask> tt; std::vector<RowTile> ttl; std::vector<AsmTask> at;
   std::vector<Launch>& LS = c->launches;
   std::vector<Msg>& MS = c->msgs;
+  std::vector<int> smalls;
   double* Lb = c->dL; double* Ub = c->dU;
   const bool MG = c->world > 1;
   const int me = c->rank;
@@ -404,6 +407,13 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         for ( int c0 = 0; c0 < meta[s].f; c0 += acols ) if ( owns( s, c0 ) ) at.push_back( { s, c0, std::min( acols, meta[s].f - c0 ) } );
       }
       if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
+    }
+    if ( c->use_small_front && !LU ) { /* small fronts: one CTA each, a single launch for the level (small_front_kernel) */
+      const int64_t s0 = ( int64_t )smalls.size();
+      std::vector<int> rest;
+      for ( int s : lv ) { if ( meta[s].k <= SF_KMAX && meta[s].f <= SF_FMAX && !is_dist( s ) ) smalls.push_back( s ); else rest.push_back( s ); }
+      if ( ( int64_t )smalls.size() > s0 ) LS.push_back( { LK_SMALL_FRONT, s0, ( int64_t )smalls.size() - s0, d, 0.0 } );
+      lv.swap( rest );
     }
     int maxk = 0; bool any_dist = false;
     for ( int s : lv ) { maxk = std::max( maxk, meta[s].k ); any_dist = any_dist || is_dist( s ); }
@@ -634,6 +644,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
   }
   if ( MG && ev_bulk_last >= 0 ) { push_nop( 0, 0 ); LS.back().wait_ev = ev_bulk_last; }     /* the factor is complete on this rank once the bulk channel has drained */
+  if ( c->small_sns.upload( smalls ) ) return B200_ERR_CUDA;
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
 
@@ -769,6 +780,7 @@ static int run_factor( b200_ctx* c ) {
         if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
         else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
+      case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;
       case LK_DIAG_S: potrf_diag_small_kernel<<<( unsigned )l.count, 256, POTRF_S_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr ); break;
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
       case LK_TRSM_MMA:
