@@ -205,6 +205,16 @@ int b200_get_stats( b200_ctx_t* c, b200_stats_t* out );
 int b200_set_profile( b200_ctx_t* c, int on );
 int b200_get_profile( b200_ctx_t* c, char* buf, size_t len );
 
+/* schedule-only context (no device, no CUDA call) and export of the static factor schedule of one rank: lets the CPU
+ * tests replay all ranks' streams / events / messages and prove the multi-GPU schedule deadlock-free
+ * (tests/test_multi_gpu_schedule.py).  stream: 0 update, 1 panel, 2 NCCL (panels, contribution blocks), 3 NCCL (bulk). */
+b200_ctx_t* b200_ctx_create_dry( int rank, int world );
+typedef struct b200_sched_entry { int kind, stream, wait_ev, record_ev, depth; int64_t first_msg, nmsg, count; } b200_sched_entry_t;
+typedef struct b200_msg { int src, dst, which; int64_t offset, count; } b200_msg_t;   /* which: 0 L, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
+int64_t b200_debug_schedule( b200_ctx_t* c, b200_sched_entry_t* out, int64_t cap );
+int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t cap );
+const char* b200_debug_kind_name( int kind );
+
 /* diagnostics for the parity tests: read back factor storage (0 = L panels, 1 = U' panels, 2 = inverse blocks) */
 int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count );
 

@@ -96,16 +96,18 @@ static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks 
 enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_FIRST, SK_FWD_STEP, SK_BWD_STEP, SK_COUNT };
 struct SLaunch { int kind; int64_t first; int64_t count; int64_t first_tile; int64_t ntiles; int depth; };
 
+static thread_local bool g_dry = false;   /* schedule-only mode: no CUDA call at all (b200_ctx_create_dry) */
+struct DryGuard { bool old; explicit DryGuard( bool v ) : old( g_dry ) { g_dry = v; } ~DryGuard() { g_dry = old; } };
 template <class T> struct DevVec {
   T* d = nullptr; size_t n = 0;
   int upload( const std::vector<T>& h ) {
     n = h.size();
-    if ( n == 0 ) return 0;
+    if ( n == 0 || g_dry ) return 0;
     CK( cudaMalloc( &d, n * sizeof( T ) ) );
     CK( cudaMemcpy( d, h.data(), n * sizeof( T ), cudaMemcpyHostToDevice ) );
     return 0;
   }
-  void release() { if ( d ) cudaFree( d ); d = nullptr; n = 0; }
+  void release() { if ( d && !g_dry ) cudaFree( d ); d = nullptr; n = 0; }
   size_t bytes() const { return n * sizeof( T ); }
 };
 
@@ -148,6 +150,7 @@ struct b200_ctx {
   void* flush_buf = nullptr; size_t flush_bytes = 0;
   bool factored = false;
   bool profile = false;
+  bool dry = false;           /* no device: the context only builds (and exports) the static schedule */
   double prof_ms[LK_COUNT] = { 0 }; int64_t prof_n[LK_COUNT] = { 0 };
   double sprof_ms[SK_COUNT] = { 0 }; int64_t sprof_n[SK_COUNT] = { 0 };
   double tiny = 0.0;
@@ -215,7 +218,27 @@ extern "C" int b200_mg_init( b200_ctx_t* c, int rank, int world, const char* id2
 }
 extern "C" int b200_mg_rank( b200_ctx_t* c, int* rank, int* world ) { if ( !c ) return B200_ERR_ARG; if ( rank ) *rank = c->rank; if ( world ) *world = c->world; return B200_OK; }
 
+/* A context without a device: b200_upload_symbolic then builds the complete launch / message schedule of rank `rank`
+ * of `world` with placeholder addresses and no CUDA call, and b200_debug_schedule / b200_debug_messages export it.
+ * tests/test_multi_gpu_schedule.py replays the schedules of all ranks on the CPU (streams, events, message matching)
+ * to prove that they cannot deadlock.  Factor / solve entry points refuse to run on such a context. */
+extern "C" b200_ctx_t* b200_ctx_create_dry( int rank, int world ) {
+  if ( world < 1 || rank < 0 || rank >= world ) return nullptr;
+  b200_ctx* c = new b200_ctx();
+  c->dry = true; c->rank = rank; c->world = world;
+  memset( &c->stats, 0, sizeof( c->stats ) );
+  memset( &c->prop, 0, sizeof( c->prop ) ); c->prop.multiProcessorCount = 148;
+  c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
+  return c;
+}
+
 static void release_symbolic( b200_ctx* c ) {
+  DryGuard dg( c->dry );
+  if ( c->dry ) {
+    c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr; c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr;
+    c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
+    return;
+  }
   cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
   cudaFree( c->dSinvF ); cudaFree( c->dSinvB ); cudaFree( c->dSinvTmp ); c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr; c->sinv_tasks.release();
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
@@ -231,6 +254,7 @@ static void release_symbolic( b200_ctx* c ) {
 
 extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   if ( !c ) return;
+  if ( c->dry ) { release_symbolic( c ); delete c; return; }
   cudaSetDevice( c->device );
   cudaStreamSynchronize( c->stream );
   release_symbolic( c );
@@ -270,8 +294,8 @@ static void add_gemm( std::vector<GemmTask>& tasks, std::vector<Tile>& big, std:
 
 extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( !c || !S ) return B200_ERR_ARG;
-  CK( cudaSetDevice( c->device ) );
-  CK( cudaStreamSynchronize( c->stream ) );
+  DryGuard dg( c->dry );
+  if ( !c->dry ) { CK( cudaSetDevice( c->device ) ); CK( cudaStreamSynchronize( c->stream ) ); }
   release_symbolic( c );
   const int ns = S->ns, n = S->n;
   const bool LU = S->kind == B200_KIND_LU;
@@ -313,8 +337,15 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   for ( int d = 0; d <= S->maxdepth; d++ ) c->w_rows[d & 1] = std::max( c->w_rows[d & 1], c->level_w[d] );
 
   /* ---- device storage */
-  size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
+  if ( c->dry ) { /* placeholder bases: only offsets matter for the exported schedule */
+    c->dL = reinterpret_cast<double*>( ( uintptr_t )1 << 40 ); c->dCB[0] = reinterpret_cast<double*>( ( uintptr_t )2 << 40 ); c->dCB[1] = reinterpret_cast<double*>( ( uintptr_t )3 << 40 );
+    c->dInv = reinterpret_cast<double*>( ( uintptr_t )4 << 40 ); c->dSinvF = reinterpret_cast<double*>( ( uintptr_t )5 << 40 ); c->dSinvB = reinterpret_cast<double*>( ( uintptr_t )6 << 40 );
+    c->dVals = reinterpret_cast<double*>( ( uintptr_t )7 << 40 );
+    if ( LU ) { c->dU = reinterpret_cast<double*>( ( uintptr_t )8 << 40 ); c->dInv2 = reinterpret_cast<double*>( ( uintptr_t )9 << 40 ); c->dSinvTmp = reinterpret_cast<double*>( ( uintptr_t )10 << 40 ); c->dPiv = reinterpret_cast<int*>( ( uintptr_t )11 << 40 ); }
+  }
   const double need = ( double )c->lsize * 8.0 * ( LU ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( LU ? 3 : 2 ) + ( double )S->nnzA * 16.0;
+  if ( !c->dry ) {
+  size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
   if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
   CK( cudaMalloc( &c->dL, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
   if ( LU ) CK( cudaMalloc( &c->dU, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
@@ -324,6 +355,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
   CK( cudaMalloc( &c->dSinvF, std::max<int64_t>( sinvoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
   if ( LU ) CK( cudaMalloc( &c->dSinvTmp, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
+  }
   c->device_bytes = ( int64_t )need;
   { std::vector<int64_t> v( S->amap, S->amap + S->nnzA ); if ( c->amap.upload( v ) ) return B200_ERR_CUDA; }
   { std::vector<int> v( S->perm, S->perm + n ); if ( c->perm.upload( v ) ) return B200_ERR_CUDA; }
@@ -649,7 +681,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
 
   c->gemm_alg_flops = g_alg_flops;
-  while ( ( int )c->events.size() < c->nevents ) { cudaEvent_t e; CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) ); c->events.push_back( e ); }
+  while ( !c->dry && ( int )c->events.size() < c->nevents ) { cudaEvent_t e; CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) ); c->events.push_back( e ); }
   /* ---- solve-block inverses: one task per (solve block, 64-column block column) */
   {
     std::vector<SinvTask> sv;
@@ -740,7 +772,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( c->sblk.upload( sb ) || c->fwd_tiles.upload( ft ) || c->bwd_tiles.upload( bt ) || c->gather_tasks.upload( gp ) ) return B200_ERR_CUDA;
   c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
                      c->asm_tasks.bytes() + c->sblk.bytes() + c->fwd_tiles.bytes() + c->bwd_tiles.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
-  CK( cudaStreamSynchronize( c->stream ) );
+  if ( !c->dry ) CK( cudaStreamSynchronize( c->stream ) );
   return B200_OK;
 }
 
@@ -838,7 +870,7 @@ static int run_factor( b200_ctx* c ) {
 }
 
 extern "C" int b200_factor_device( b200_ctx_t* c, const double* d_vals ) {
-  if ( !c || !c->dL ) return B200_ERR_STATE;
+  if ( !c || !c->dL || c->dry ) return B200_ERR_STATE;
   CK( cudaSetDevice( c->device ) );
   if ( d_vals != c->dVals && c->nnzA > 0 ) CK( cudaMemcpyAsync( c->dVals, d_vals, ( size_t )c->nnzA * 8, cudaMemcpyDeviceToDevice, c->stream ) );
   if ( c->kind == B200_KIND_LU && c->tiny == 0.0 ) c->tiny = 1.5e-8;
@@ -847,7 +879,7 @@ extern "C" int b200_factor_device( b200_ctx_t* c, const double* d_vals ) {
 }
 
 extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
-  if ( !c || !c->dL ) return B200_ERR_STATE;
+  if ( !c || !c->dL || c->dry ) return B200_ERR_STATE;
   CK( cudaSetDevice( c->device ) );
   if ( c->kind == B200_KIND_LU ) { /* static-pivot threshold: sqrt(eps) * max|a_ij| */
     double mx = 0; for ( int64_t e = 0; e < c->nnzA; e++ ) mx = std::max( mx, std::fabs( vals[e] ) );
@@ -1245,3 +1277,23 @@ extern "C" double b200_bench_dgemm_bulk_variant( b200_ctx_t* c, int variant, int
     default: return -1.0;
   }
 }
+
+/* ---- export of the static factor schedule (diagnostics; see b200_ctx_create_dry) */
+extern "C" int64_t b200_debug_schedule( b200_ctx_t* c, b200_sched_entry_t* out, int64_t cap ) {
+  if ( !c ) return -1;
+  const int64_t n = ( int64_t )c->launches.size();
+  for ( int64_t i = 0; i < n && i < cap; i++ ) {
+    const Launch& l = c->launches[i];
+    const bool comm = l.kind == LK_XFER_CB || l.kind == LK_BCAST || l.kind == LK_GATHER;
+    out[i].kind = l.kind; out[i].stream = l.stream; out[i].wait_ev = l.wait_ev; out[i].record_ev = l.record_ev; out[i].depth = l.depth;
+    out[i].first_msg = comm ? l.first : -1; out[i].nmsg = comm ? l.count : 0; out[i].count = l.count;
+  }
+  return n;
+}
+extern "C" int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t cap ) {
+  if ( !c ) return -1;
+  const int64_t n = ( int64_t )c->msgs.size();
+  for ( int64_t i = 0; i < n && i < cap; i++ ) { const Msg& m = c->msgs[i]; out[i].src = m.src; out[i].dst = m.dst; out[i].which = m.which; out[i].offset = m.off; out[i].count = m.cnt; }
+  return n;
+}
+extern "C" const char* b200_debug_kind_name( int kind ) { return kind >= 0 && kind < LK_COUNT ? kind_name[kind] : "?"; }

@@ -288,7 +288,8 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
     if ( c->nv > 0.93 * G[nl]->nv ) { graph_free( c ); free( cmap ); break; }
     CM[nl] = cmap; G[nl + 1] = c; nl++;
   }
-  const double ub = 1.20;
+  static double ub_env = -1.0; if ( ub_env < 0 ) { const char* e = getenv( "B200_ND_UB" ); ub_env = e ? atof( e ) : 1.40; }     /* measured with 4 starts: 1.40 beats 1.20 / 1.30 / 1.50 on 128^3, 96^3, 2-D 1024^2 and 27-pt 64^3 (fill falls when a side may hold up to 70 %) */
+  const double ub = ub_env;
   int maxpw = ( int )( ub * total / 2.0 ) + 1;
   /* initial separators on the coarsest graph */
   graph_t* gc = G[nl];
@@ -302,7 +303,8 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
   heap_t H[2];
   heap_init( &H[0], g0->nv ); heap_init( &H[1], g0->nv );
   long bestscore = -1; int bestpw[3] = {0, 0, 0};
-  int ntries = cnv < 12 ? cnv : 12;
+  static int tries_env = -1; if ( tries_env < 0 ) { const char* e = getenv( "B200_ND_TRIES" ); tries_env = e ? atoi( e ) : 12; }
+  int ntries = cnv < tries_env ? cnv : tries_env;
   for ( int t = 0; t < ntries; t++ ) {
     int seed = rng_next( rng ) % ( uint32_t )cnv;
     int pw[3];
@@ -396,9 +398,34 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
     return;
   }
   int* where = malloc( sizeof( int ) * nv );
-  uint32_t rng = 0x12345u + 2654435761u * ( uint32_t )first + 40503u * ( uint32_t )nv;
-  multilevel_separator( g, where, &rng );
   int n0 = 0, n1 = 0, n2 = 0;
+  {
+    /* Multi-start on the large subgraphs: the top separators decide the fill (their fronts cost ~|S|^3), and one
+     * multilevel run is a lottery (128^3: 1.35e13 ... 1.80e13 flops depending on the balance bound alone).  The
+     * top of the recursion has idle cores anyway (1, 2, 4 ... subgraphs), so R independent runs with different
+     * seeds go out as tasks and the smallest separator (with a mild imbalance penalty) wins; ties go to the
+     * lower run index, so the result does not depend on the number of threads. */
+    static int starts_env = -1; if ( starts_env < 0 ) { const char* e = getenv( "B200_ND_STARTS" ); starts_env = e ? atoi( e ) : 4; if ( starts_env < 1 ) starts_env = 1; if ( starts_env > 16 ) starts_env = 16; }
+    const int R = nv >= 30000 ? starts_env : 1;
+    int* cand[16]; double score[16];
+    for ( int r = 0; r < R; r++ ) cand[r] = r == 0 ? where : malloc( sizeof( int ) * nv );
+    for ( int r = 0; r < R; r++ ) {
+      #pragma omp task default(shared) firstprivate(r) if ( R > 1 )
+      {
+        uint32_t rng = 0x12345u + 2654435761u * ( uint32_t )first + 40503u * ( uint32_t )nv + 0x9E3779B9u * ( uint32_t )r;
+        multilevel_separator( g, cand[r], &rng );
+        long c0 = 0, c1 = 0, c2 = 0;
+        for ( int v = 0; v < nv; v++ ) { if ( cand[r][v] == 0 ) c0++; else if ( cand[r][v] == 1 ) c1++; else c2++; }
+        const double imb = ( c0 + c1 ) > 0 ? ( double )( c0 > c1 ? c0 - c1 : c1 - c0 ) / ( double )( c0 + c1 ) : 1.0;
+        score[r] = ( c0 == 0 || c1 == 0 ) ? 1e300 : ( double )c2 * ( 1.0 + 2.0 * imb * imb );
+      }
+    }
+    #pragma omp taskwait
+    int best = 0;
+    for ( int r = 1; r < R; r++ ) if ( score[r] < score[best] ) best = r;
+    if ( best != 0 ) memcpy( where, cand[best], sizeof( int ) * nv );
+    for ( int r = 1; r < R; r++ ) free( cand[r] );
+  }
   for ( int v = 0; v < nv; v++ ) { if ( where[v] == 0 ) n0++; else if ( where[v] == 1 ) n1++; else n2++; }
   if ( n0 == 0 || n1 == 0 ) {
     /* bisection failed (e.g. a clique): order what is left by degree-sorted natural order in chunks */
