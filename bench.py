@@ -169,7 +169,14 @@ def main():
     if world > 1:
         s.join(rank, world, dist=dist)
     host_threads = max(1, (os.cpu_count() or 8) // world)
-    t0 = time.perf_counter(); S = s.analyze(n, cp, ri, m.KIND_CHOLESKY, threads=host_threads); t_analyze = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if world > 1:   # rank 0 orders with all host cores and broadcasts the permutation; every rank then runs the same symbolic analysis on it
+        perm = m.shared_ordering(n, cp, ri, m.KIND_CHOLESKY, rank, world, dist, threads=os.cpu_count() or 8)
+        S = s.analyze(n, cp, ri, m.KIND_CHOLESKY, perm=perm, threads=host_threads)
+    else:
+        perm = None
+        S = s.analyze(n, cp, ri, m.KIND_CHOLESKY, threads=host_threads)
+    t_analyze = time.perf_counter() - t0
     F = S.flops
     ctx = s.ctx
     d_vals = L.b200_dev_alloc(ctx, v.nbytes); L.b200_dev_upload(ctx, d_vals, v.ctypes.data, v.nbytes)
@@ -274,7 +281,7 @@ def main():
         # ---- e2e at N > 1: the C-ABI shim with HOST buffers on every rank (H2D of the values / b and D2H of x inside the timed calls);
         # the plugin row itself is single-process (SOLVER_SINGLE_THREADED_ONLY), see DESIGN.md 7
         s2 = m.Solver(device=local); s2.join(rank, world, dist=dist)
-        s2.analyze(n, cp, ri, m.KIND_CHOLESKY, threads=host_threads)
+        s2.analyze(n, cp, ri, m.KIND_CHOLESKY, perm=perm, threads=host_threads)
         ftimes, etimes = [], []
         for i in range(2 + 3):
             dist.barrier(); t = time.perf_counter(); rc = s2.factor(v); tf = time.perf_counter() - t

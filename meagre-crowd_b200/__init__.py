@@ -267,6 +267,28 @@ def analyze(n, colptr, rowidx, kind=KIND_CHOLESKY, ordering=ORDER_ND, perm=None,
     return S
 
 
+def shared_ordering(n, colptr, rowidx, kind, rank, world, dist, threads=0):
+    """one process per GPU: rank 0 computes the fill-reducing ordering with all its host threads and broadcasts it
+    (torch.distributed), so that N ranks do not run N copies of the most expensive host step on N-times fewer cores each.
+    Every rank (rank 0 included) then runs the rest of the analysis on the GIVEN permutation -- the same code path
+    everywhere, hence bit-identical symbolic structures.  Returns the permutation (numpy int32)."""
+    import torch
+    if world == 1:
+        S = analyze(n, colptr, rowidx, kind, threads=threads)
+        perm = sym_array(S, "perm", n, np.int32).copy()
+        lib().b200_symbolic_free(S)
+        return perm
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    if rank == 0:
+        S = analyze(n, colptr, rowidx, kind, threads=threads)
+        t = torch.from_numpy(sym_array(S, "perm", n, np.int32).copy()).to(dev)
+        lib().b200_symbolic_free(S)
+    else:
+        t = torch.empty(n, dtype=torch.int32, device=dev)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
 def panel_view(flat, offset, f, k):
     """f x k view of a factor panel: column-major, leading dimension f rounded up to even"""
     ld = (int(f) + 1) & ~1
@@ -309,6 +331,7 @@ class Solver:
             raise RuntimeError("b200_mg_init: " + self.err())
 
     def analyze(self, n, colptr, rowidx, kind=KIND_CHOLESKY, **kw):
+        """kw: ordering / perm / relax / nd_leaf / threads of analyze(); perm = a given elimination order (e.g. shared_ordering)"""
         if self.S:
             self.L.b200_symbolic_free(self.S)
         self.S = analyze(n, colptr, rowidx, kind, **kw)

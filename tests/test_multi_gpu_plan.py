@@ -159,3 +159,40 @@ def test_two_processes_derive_the_same_plan_and_matching_messages(mc, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+WORKER2 = r'''
+import os, sys, hashlib, numpy as np
+sys.path.insert(0, {root!r})
+import torch.distributed as dist, torch
+import __graft_entry__ as g
+m = g.load_package(); L = m.lib()
+from meagre_crowd_b200 import stencils
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n, cp, ri, v = stencils.poisson3d_upper(20)
+perm = m.shared_ordering(n, cp, ri, m.KIND_CHOLESKY, rank, world, dist, threads=2)
+assert sorted(perm.tolist()) == list(range(n))
+S = m.analyze(n, cp, ri, perm=perm, threads=1 + rank)
+s = S.contents
+h = hashlib.sha256()
+for name, ln, dt in (("perm", n, np.int32), ("sn_start", s.ns + 1, np.int32), ("sn_parent", s.ns, np.int32), ("rowptr", s.ns + 1, np.int64), ("lptr", s.ns + 1, np.int64), ("cbptr", s.ns, np.int64)):
+    h.update(m.sym_array(S, name, ln, dt).tobytes())
+h.update(m.sym_array(S, "rowidx", int(m.sym_array(S, "rowptr", s.ns + 1, np.int64)[-1]), np.int32).tobytes())
+d = [torch.zeros(32, dtype=torch.uint8) for _ in range(world)]
+dist.all_gather(d, torch.from_numpy(np.frombuffer(h.digest(), dtype=np.uint8).copy()))
+assert all(torch.equal(d[0], x) for x in d), "ranks built different symbolic structures from the shared ordering"
+print("rank", rank, "ok", s.ns, s.nnzL)
+dist.destroy_process_group()
+'''
+
+
+def test_shared_ordering_gives_identical_analyses_on_every_rank(mc, tmp_path):
+    """bench.py at N > 1: rank 0 orders, broadcasts the permutation, every rank analyses the given order"""
+    script = tmp_path / "worker2.py"
+    script.write_text(WORKER2.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29535", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
