@@ -156,7 +156,8 @@ static void node_fm( const graph_t* g, int* where, int* pw, int maxpw, int npass
       if ( where[v] == 2 ) { heap_upsert( &H[0], v, sep_gain( g, where, v, 0 ) ); heap_upsert( &H[1], v, sep_gain( g, where, v, 1 ) ); nsepv++; }
     }
     if ( nsepv == 0 ) return;
-    const int limit = nsepv < 40 ? 40 + nsepv : ( nsepv / 4 + 60 > 400 ? 400 : nsepv / 4 + 60 );
+    static int fm_cap = -1; if ( fm_cap < 0 ) { const char* e = getenv( "B200_FM_CAP" ); fm_cap = e ? atoi( e ) : 400; }
+    const int limit = nsepv < 40 ? 40 + nsepv : ( nsepv / 4 + 60 > fm_cap ? fm_cap : nsepv / 4 + 60 );
     int nmoves = 0, npulled = 0, bestmoves = 0;
     int bestsep = pw[2], bestdiff = abs( pw[0] - pw[1] );
     int cursep = pw[2];
@@ -322,7 +323,8 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
     for ( int v = 0; v < gf->nv; v++ ) wf[v] = cur[CM[l][v]];
     free( cur ); cur = wf;
     /* projected separators are thick: vertices with no neighbour on one side can leave for free */
-    node_fm( gf, cur, pw, maxpw, gf->nv > 200000 ? 3 : 5, H, locked, pulled, moves );
+    static int fm_big = -1, fm_small = -1; if ( fm_big < 0 ) { const char* e = getenv( "B200_FM_PASSES_BIG" ); fm_big = e ? atoi( e ) : 3; e = getenv( "B200_FM_PASSES" ); fm_small = e ? atoi( e ) : 5; }
+    node_fm( gf, cur, pw, maxpw, gf->nv > 200000 ? fm_big : fm_small, H, locked, pulled, moves );
     graph_free( G[l + 1] ); free( CM[l] );
   }
   if ( nl == 0 ) { memcpy( where0, cur, sizeof( int ) * g0->nv ); free( cur ); }
@@ -427,6 +429,7 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
     for ( int r = 1; r < R; r++ ) free( cand[r] );
   }
   for ( int v = 0; v < nv; v++ ) { if ( where[v] == 0 ) n0++; else if ( where[v] == 1 ) n1++; else n2++; }
+  { static int verbose = -1; if ( verbose < 0 ) verbose = getenv( "B200_ND_VERBOSE" ) != NULL; if ( verbose && nv >= 20000 ) fprintf( stderr, "nd depth %d: nv=%d -> %d | %d | sep %d\n", depth, nv, n0, n1, n2 ); }
   if ( n0 == 0 || n1 == 0 ) {
     /* bisection failed (e.g. a clique): order what is left by degree-sorted natural order in chunks */
     if ( nv <= 4096 ) {
