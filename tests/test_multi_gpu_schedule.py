@@ -53,3 +53,72 @@ def test_replay_detects_a_broken_schedule(mc):
     with pytest.raises(AssertionError):
         sched_sim.check(bad)
     mc.lib().b200_symbolic_free(S)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_every_rank_ends_up_with_the_whole_factor(mc, world):
+    """the sweeps run replicated, so after the factorization every rank must hold every column of L and every 64x64 inverse
+    block: either it computed them (b200_plan_col_owner) or a message delivered them.  Checked from the exported messages."""
+    import numpy as np
+    from helpers import sym_dict
+    n, cp, ri, v = stencils.poisson3d_upper(22)
+    S = mc.analyze(n, cp, ri)
+    d = sym_dict(mc, S); ns = d["ns"]; L = mc.lib()
+    os.environ["B200_MIN_DIST_FRONT"] = "128"
+    try:
+        sch = [sched_sim.export(mc, S, world, r) for r in range(world)]
+        pl = L.b200_plan_create(S, world, 128)
+    finally:
+        del os.environ["B200_MIN_DIST_FRONT"]
+    sched_sim.check(sch)
+    st, rp, lp = d["sn_start"], d["rowptr"], d["lptr"]
+    k = np.diff(st); f = np.diff(rp); ld = (f + 1) & ~1
+    nblk = (k + 63) // 64; blk0 = np.concatenate([[0], np.cumsum(nblk)])
+    invsz = (k // 64) * 4096 + (k % 64) ** 2; invp = np.concatenate([[0], np.cumsum(invsz)])
+    assert np.array_equal(lp[1:] - lp[:-1], ld * k)
+    for r in range(world):
+        have = np.zeros(n, dtype=bool); have_inv = np.zeros(blk0[-1], dtype=bool)
+        for s in range(ns):
+            for c in range(k[s]):
+                if L.b200_plan_col_owner(pl, S, s, int(c)) == r:
+                    have[st[s] + c] = True; have_inv[blk0[s] + c // 64] = True
+        for (src, dst, which, off, cnt) in sch[r][1]:
+            if dst != r or which > 1:
+                continue
+            if which == 0:
+                s = int(np.searchsorted(lp, off, side="right") - 1)
+                while cnt > 0:
+                    rel = off - lp[s]
+                    assert rel % ld[s] == 0, "L message does not start at a column"
+                    c0 = rel // ld[s]; nc = min(k[s] - c0, cnt // ld[s])
+                    assert nc > 0 and (cnt >= ld[s] * nc)
+                    have[st[s] + c0: st[s] + c0 + nc] = True
+                    off += nc * ld[s]; cnt -= nc * ld[s]; s += 1
+            else:
+                s = int(np.searchsorted(invp, off, side="right") - 1)
+                while cnt > 0:
+                    rel = off - invp[s]
+                    assert rel % 4096 == 0, "inverse message does not start at a block"
+                    b0 = rel // 4096
+                    take = min(invsz[s] - rel, cnt)
+                    nb = (take + 4095) // 4096
+                    have_inv[blk0[s] + b0: blk0[s] + b0 + nb] = True
+                    off += take; cnt -= take; s += 1
+        assert have.all(), f"rank {r} lacks {np.count_nonzero(~have)} columns of L"
+        assert have_inv.all(), f"rank {r} lacks {np.count_nonzero(~have_inv)} inverse blocks"
+    L.b200_plan_free(pl); L.b200_symbolic_free(S)
+
+
+def test_multi_gpu_lu_is_refused_not_silently_wrong(mc):
+    """the distributed extend-add of the U' part is not built: the shim must say so instead of producing a schedule"""
+    n, cp, ri, v = stencils.convdiff27_full(8)
+    S = mc.analyze(n, cp, ri, mc.KIND_LU)
+    L = mc.lib()
+    c = L.b200_ctx_create_dry(0, 2)
+    assert L.b200_upload_symbolic(c, S) == mc.B200_ERR_ARG and b"Cholesky only" in L.b200_last_error()
+    L.b200_ctx_destroy(c)
+    c = L.b200_ctx_create_dry(0, 1)            # one rank: LU schedules fine
+    assert L.b200_upload_symbolic(c, S) == mc.B200_OK
+    assert L.b200_factor_host(c, v.ctypes.data) == mc.B200_ERR_STATE      # and a schedule-only context never computes
+    L.b200_ctx_destroy(c)
+    L.b200_symbolic_free(S)
