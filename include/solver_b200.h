@@ -214,6 +214,8 @@ typedef struct b200_msg { int src, dst, which; int64_t offset, count; } b200_msg
 int64_t b200_debug_schedule( b200_ctx_t* c, b200_sched_entry_t* out, int64_t cap );
 int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t cap );
 const char* b200_debug_kind_name( int kind );
+typedef struct b200_access { int launch, which, write; int64_t offset, count; } b200_access_t;   /* conservative interval a compute launch reads (0) or writes (1) */
+int64_t b200_debug_accesses( b200_ctx_t* c, b200_access_t* out, int64_t cap );
 
 /* diagnostics for the parity tests: read back factor storage (0 = L panels, 1 = U' panels, 2 = inverse blocks) */
 int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count );

@@ -151,6 +151,8 @@ struct b200_ctx {
   bool factored = false;
   bool profile = false;
   bool dry = false;           /* no device: the context only builds (and exports) the static schedule */
+  /* host copies of the task lists, kept only by a schedule-only context (b200_debug_accesses) */
+  std::vector<GemmTask> h_gt; std::vector<Tile> h_tb; std::vector<DiagTask> h_dt; std::vector<TrsmTask> h_tt; std::vector<RowTile> h_ttl; std::vector<AsmTask> h_at; std::vector<int> h_small, h_child; std::vector<SnMeta> h_meta;
   double prof_ms[LK_COUNT] = { 0 }; int64_t prof_n[LK_COUNT] = { 0 };
   double sprof_ms[SK_COUNT] = { 0 }; int64_t sprof_n[SK_COUNT] = { 0 };
   double tiny = 0.0;
@@ -676,6 +678,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
   }
   if ( MG && ev_bulk_last >= 0 ) { push_nop( 0, 0 ); LS.back().wait_ev = ev_bulk_last; }     /* the factor is complete on this rank once the bulk channel has drained */
+  if ( c->dry ) { c->h_gt = gt; c->h_tb = tb; c->h_dt = dt; c->h_tt = tt; c->h_ttl = ttl; c->h_at = at; c->h_small = smalls; c->h_child = child_list; c->h_meta = meta; }
   if ( c->small_sns.upload( smalls ) ) return B200_ERR_CUDA;
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
        c->trsm_tasks.upload( tt ) || c->trsm_tiles.upload( ttl ) || c->asm_tasks.upload( at ) ) return B200_ERR_CUDA;
@@ -1297,3 +1300,61 @@ extern "C" int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t 
   return n;
 }
 extern "C" const char* b200_debug_kind_name( int kind ) { return kind >= 0 && kind < LK_COUNT ? kind_name[kind] : "?"; }
+
+/* every memory range a compute launch of the factor schedule may read or write, as conservative intervals of doubles inside
+ * one of the four buffers (0 L, 1 inverse blocks, 2/3 contribution-block arena 0/1); schedule-only contexts only.
+ * tests/sched_sim.py uses it to prove that every message is ordered against the launches that touch the same data. */
+extern "C" int64_t b200_debug_accesses( b200_ctx_t* c, b200_access_t* out, int64_t cap ) {
+  if ( !c || !c->dry ) return -1;
+  int64_t n = 0;
+  auto emit = [&]( int launch, const void* p, int64_t cnt, int write ) {
+    if ( !p || cnt <= 0 ) return;
+    const uintptr_t a = ( uintptr_t )p; const int tag = ( int )( a >> 40 );
+    const int which = tag == 1 ? 0 : tag == 4 ? 1 : tag == 2 ? 2 : tag == 3 ? 3 : -1;
+    if ( which < 0 ) return;                              /* other buffers (U', pivots, solve inverses) never travel */
+    if ( n < cap ) { out[n].launch = launch; out[n].which = which; out[n].write = write; out[n].offset = ( int64_t )( ( a - ( ( uintptr_t )tag << 40 ) ) / 8 ); out[n].count = cnt; }
+    n++;
+  };
+  for ( size_t i = 0; i < c->launches.size(); i++ ) {
+    const Launch& l = c->launches[i]; const int li = ( int )i;
+    switch ( l.kind ) {
+      case LK_MEMSET_CB: emit( li, c->dCB[l.depth & 1] + l.first, l.count, 1 ); break;
+      case LK_ASM:
+        for ( int64_t t = l.first; t < l.first + l.count; t++ ) {
+          const AsmTask& a = c->h_at[t]; const SnMeta& P = c->h_meta[a.parent];
+          const int u = P.f - P.k; const int64_t ldu = ( u + 1 ) & ~1;
+          const int p_hi = std::min( a.col0 + a.ncols, P.k );
+          if ( a.col0 < p_hi ) emit( li, c->dL + P.lptr + ( int64_t )a.col0 * P.ld, ( int64_t )( p_hi - a.col0 ) * P.ld, 1 );
+          const int j_lo = std::max( a.col0, P.k ) - P.k, j_hi = a.col0 + a.ncols - P.k;
+          if ( j_lo < j_hi ) emit( li, c->dCB[l.depth & 1] + P.cbptr + ( int64_t )j_lo * ldu, ( int64_t )( j_hi - j_lo ) * ldu, 1 );
+          for ( int ci = P.child_begin; ci < P.child_end; ci++ ) { const SnMeta& C = c->h_meta[c->h_child[ci]]; const int uc = C.f - C.k; if ( uc > 0 ) emit( li, c->dCB[( l.depth + 1 ) & 1] + C.cbptr, ( int64_t )uc * ( ( uc + 1 ) & ~1 ), 0 ); }
+        }
+        break;
+      case LK_DIAG: case LK_DIAG_S:
+        for ( int64_t t = l.first; t < l.first + l.count; t++ ) { const DiagTask& d = c->h_dt[t]; emit( li, d.A, ( int64_t )( d.nb - 1 ) * d.lda + d.nb, 1 ); emit( li, d.inv, ( int64_t )d.nb * d.nb, 1 ); }
+        break;
+      case LK_TRSM:
+        for ( int64_t t = l.first; t < l.first + l.count; t++ ) { const TrsmTask& x = c->h_tt[c->h_ttl[t].task]; emit( li, x.B, ( int64_t )( x.nb - 1 ) * x.ldb + x.m, 1 ); emit( li, x.T, ( int64_t )x.nb * x.nb, 0 ); }
+        break;
+      case LK_GEMM_BIG: case LK_TRSM_MMA: {
+        int last = -1;
+        for ( int64_t t = l.first; t < l.first + l.count; t++ ) {
+          const int id = c->h_tb[t].task; if ( id == last ) continue; last = id;
+          const GemmTask& g = c->h_gt[id];
+          emit( li, g.C, ( int64_t )( g.N - 1 ) * g.ldc + g.M, 1 );
+          emit( li, g.A, ( int64_t )( g.K - 1 ) * g.lda + g.M, 0 );
+          emit( li, g.B, ( int64_t )( g.K - 1 ) * g.ldb + g.N, 0 );
+        }
+        break; }
+      case LK_SMALL_FRONT:
+        for ( int64_t t = l.first; t < l.first + l.count; t++ ) {
+          const SnMeta& S = c->h_meta[c->h_small[t]]; const int u = S.f - S.k;
+          emit( li, c->dL + S.lptr, ( int64_t )S.k * S.ld, 1 ); emit( li, c->dInv + S.invptr, ( int64_t )S.k * S.k, 1 );
+          if ( u > 0 ) emit( li, c->dCB[l.depth & 1] + S.cbptr, ( int64_t )u * ( ( u + 1 ) & ~1 ), 1 );
+        }
+        break;
+      default: break;
+    }
+  }
+  return n;
+}

@@ -16,7 +16,7 @@ import ctypes as C
 COMM_STREAMS = (2, 3)
 
 
-def export(mc, S, world, rank):
+def export(mc, S, world, rank, with_accesses=False):
     L = mc.lib()
     c = L.b200_ctx_create_dry(rank, world)
     assert c, "dry context"
@@ -29,6 +29,13 @@ def export(mc, S, world, rank):
                      msgs=list(range(le[i].first_msg, le[i].first_msg + le[i].nmsg)) if le[i].nmsg > 0 and le[i].first_msg >= 0 else [],
                      name=L.b200_debug_kind_name(le[i].kind).decode()) for i in range(nl)]
     msgs = [(me[i].src, me[i].dst, me[i].which, me[i].offset, me[i].count) for i in range(nm)]
+    if with_accesses:
+        import numpy as np
+        na = L.b200_debug_accesses(c, None, 0)
+        ae = (mc.b200_access_t * max(na, 1))(); L.b200_debug_accesses(c, ae, na)
+        acc = np.frombuffer(ae, dtype=np.dtype([("launch", "<i4"), ("which", "<i4"), ("write", "<i4"), ("pad", "<i4"), ("offset", "<i8"), ("count", "<i8")]), count=na).copy()
+        L.b200_ctx_destroy(c)
+        return launches, msgs, acc
     L.b200_ctx_destroy(c)
     return launches, msgs
 
@@ -98,3 +105,48 @@ def check(schedules):
     stuck = {r: [(i, schedules[r][0][i]["name"], schedules[r][0][i]["stream"], schedules[r][0][i]["depth"]) for st, dq in by_stream[r].items() for i in list(dq)[:1]] for r in range(world) if any(by_stream[r].values())}
     assert not stuck, f"schedule deadlocks; heads of the blocked streams: {stuck}"
     return dict(launches=[len(s[0]) for s in schedules], messages=[len(s[1]) for s in schedules], nccl_bytes=nbytes, rounds=rounds)
+
+
+def check_hazards(launches, msgs, acc, rank):
+    """Every message must be ORDERED (stream order / events) against every compute launch of the same rank that touches the
+    same memory: a received range against its readers and writers, a sent range against its writers.  Accesses are the
+    conservative intervals of b200_debug_accesses.  Returns the number of (message, access) pairs examined."""
+    import numpy as np
+    m = len(launches)
+    anc = [0] * m                      # bit j of anc[i]: launch j happens before launch i
+    last_in_stream = {}; rec_at = {}
+    for i, l in enumerate(launches):
+        a = 0
+        p = last_in_stream.get(l["stream"])
+        if p is not None:
+            a |= anc[p] | (1 << p)
+        if l["wait"] >= 0:
+            q = rec_at[l["wait"]]; a |= anc[q] | (1 << q)
+        anc[i] = a
+        last_in_stream[l["stream"]] = i
+        if l["rec"] >= 0:
+            rec_at[l["rec"]] = i
+    by_which = {w: acc[acc["which"] == w] for w in range(4)}
+    pairs = 0
+    for ci, l in enumerate(launches):
+        for q in l["msgs"]:
+            src, dst, which, off, cnt = msgs[q]
+            a = by_which[which]
+            if len(a) == 0:
+                continue
+            hit = a[(a["offset"] < off + cnt) & (a["offset"] + a["count"] > off)]
+            if src == rank:
+                hit = hit[hit["write"] == 1]           # a send only conflicts with writers
+            for li in np.unique(hit["launch"]):
+                li = int(li); pairs += 1
+                ordered = (anc[li] >> ci) & 1 or (anc[ci] >> li) & 1
+                assert ordered, (f"rank {rank}: {'send' if src == rank else 'receive'} of buffer {which} [{off}, {off + cnt}) in launch {ci} ({l['name']}, depth {l['depth']}) "
+                                 f"is not ordered against launch {li} ({launches[li]['name']}, stream {launches[li]['stream']}, depth {launches[li]['depth']}) that touches the same range")
+                # data that arrives must arrive BEFORE it is used.  L and the inverse blocks are written once per factorization;
+                # the contribution-block arenas are reused by every second tree level, so there the rule binds the readers of the
+                # SAME level only (an earlier level's reader must merely be ordered: it read the slot's previous content)
+                if dst == rank and (which < 2 or launches[li]["depth"] == l["depth"]):
+                    rd = hit[(hit["launch"] == li) & (hit["write"] == 0)]
+                    if len(rd):
+                        assert (anc[li] >> ci) & 1, f"rank {rank}: launch {li} ({launches[li]['name']}) reads [{off}, {off + cnt}) of buffer {which} before the message in launch {ci} delivers it"
+    return pairs

@@ -122,3 +122,45 @@ def test_multi_gpu_lu_is_refused_not_silently_wrong(mc):
     assert L.b200_factor_host(c, v.ctypes.data) == mc.B200_ERR_STATE      # and a schedule-only context never computes
     L.b200_ctx_destroy(c)
     L.b200_symbolic_free(S)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("gen,min_front", [(lambda: stencils.poisson3d_upper(22), 128), (lambda: stencils.poisson2d_upper(90, 60), 48)])
+def test_messages_are_ordered_against_the_launches_that_touch_the_same_data(mc, world, gen, min_front):
+    """no race between NCCL traffic and compute: happens-before (stream order + events) must relate every message to every
+    launch of its rank whose conservative access intervals overlap the message's range; arriving data precedes its readers"""
+    n, cp, ri, v = gen()
+    S = mc.analyze(n, cp, ri)
+    os.environ["B200_MIN_DIST_FRONT"] = str(min_front)
+    try:
+        sch = [sched_sim.export(mc, S, world, r, with_accesses=True) for r in range(world)]
+    finally:
+        del os.environ["B200_MIN_DIST_FRONT"]
+    sched_sim.check([(a, b) for a, b, c in sch])
+    total = sum(sched_sim.check_hazards(ls, ms, acc, r) for r, (ls, ms, acc) in enumerate(sch))
+    assert total > 0
+    mc.lib().b200_symbolic_free(S)
+
+
+def test_hazard_check_notices_a_missing_wait(mc):
+    """the checker itself: dropping the wait that orders a trailing update after the panel's arrival must be reported"""
+    import copy
+    n, cp, ri, v = stencils.poisson3d_upper(22)
+    S = mc.analyze(n, cp, ri)
+    os.environ["B200_MIN_DIST_FRONT"] = "128"
+    try:
+        sch = [sched_sim.export(mc, S, 2, r, with_accesses=True) for r in range(2)]
+    finally:
+        del os.environ["B200_MIN_DIST_FRONT"]
+    caught = 0; tried = 0
+    for r, (ls, ms, acc) in enumerate(sch):
+        recv_events = {l["rec"] for l in ls if l["msgs"] and any(ms[q][1] == r for q in l["msgs"]) and l["rec"] >= 0}
+        for i, l in enumerate(ls):
+            if l["wait"] in recv_events and l["stream"] in (0, 1):
+                bad = copy.deepcopy(ls); bad[i]["wait"] = -1; tried += 1
+                try:
+                    sched_sim.check_hazards(bad, ms, acc, r)
+                except AssertionError:
+                    caught += 1
+    assert tried > 0 and caught > 0, (tried, caught)
+    mc.lib().b200_symbolic_free(S)
