@@ -209,7 +209,9 @@ int b200_get_profile( b200_ctx_t* c, char* buf, size_t len );
  * tests replay all ranks' streams / events / messages and prove the multi-GPU schedule deadlock-free
  * (tests/test_multi_gpu_schedule.py).  stream: 0 update, 1 panel, 2 NCCL (panels, contribution blocks), 3 NCCL (bulk). */
 b200_ctx_t* b200_ctx_create_dry( int rank, int world );
-typedef struct b200_sched_entry { int kind, stream, wait_ev, record_ev, depth; int64_t first_msg, nmsg, count; } b200_sched_entry_t;
+typedef struct b200_sched_entry { int kind, stream, wait_ev, record_ev, depth; int64_t first_msg, nmsg, count;
+  double flops, kavg, bytes;   /* schedule-only contexts: executed flops and flop-weighted K of a DMMA launch, bytes written by memset / extend-add (cost models) */
+} b200_sched_entry_t;
 typedef struct b200_msg { int src, dst, which; int64_t offset, count; } b200_msg_t;   /* which: 0 L, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
 int64_t b200_debug_schedule( b200_ctx_t* c, b200_sched_entry_t* out, int64_t cap );
 int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t cap );

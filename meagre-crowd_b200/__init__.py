@@ -74,7 +74,7 @@ class b200_xfer_t(C.Structure):
 
 class b200_sched_entry_t(C.Structure):
     _fields_ = [("kind", C.c_int), ("stream", C.c_int), ("wait_ev", C.c_int), ("record_ev", C.c_int), ("depth", C.c_int),
-                ("first_msg", C.c_int64), ("nmsg", C.c_int64), ("count", C.c_int64)]
+                ("first_msg", C.c_int64), ("nmsg", C.c_int64), ("count", C.c_int64), ("flops", C.c_double), ("kavg", C.c_double), ("bytes", C.c_double)]
 
 
 class b200_access_t(C.Structure):

@@ -1290,6 +1290,20 @@ extern "C" int64_t b200_debug_schedule( b200_ctx_t* c, b200_sched_entry_t* out, 
     const bool comm = l.kind == LK_XFER_CB || l.kind == LK_BCAST || l.kind == LK_GATHER;
     out[i].kind = l.kind; out[i].stream = l.stream; out[i].wait_ev = l.wait_ev; out[i].record_ev = l.record_ev; out[i].depth = l.depth;
     out[i].first_msg = comm ? l.first : -1; out[i].nmsg = comm ? l.count : 0; out[i].count = l.count;
+    out[i].flops = 0; out[i].kavg = 0; out[i].bytes = 0;
+    if ( c->dry && ( l.kind == LK_GEMM_BIG || l.kind == LK_TRSM_MMA ) ) {
+      double fl = 0, fk = 0;
+      for ( int64_t t = l.first; t < l.first + l.count; t++ ) { const Tile& tl = c->h_tb[t]; const GemmTask& g = c->h_gt[tl.task];
+        const double mm = std::min( GEMM_BM, g.M - tl.tm * GEMM_BM ), nn = std::min( GEMM_BN, g.N - tl.tn * GEMM_BN ); const double f = 2.0 * mm * nn * g.K; fl += f; fk += f * g.K; }
+      out[i].flops = fl; out[i].kavg = fl > 0 ? fk / fl : 0;
+    } else if ( c->dry && l.kind == LK_MEMSET_CB ) out[i].bytes = 8.0 * l.count;
+    else if ( c->dry && l.kind == LK_ASM ) {
+      double b = 0;
+      for ( int64_t t = l.first; t < l.first + l.count; t++ ) { const AsmTask& a = c->h_at[t]; const SnMeta& P = c->h_meta[a.parent];
+        for ( int ci = P.child_begin; ci < P.child_end; ci++ ) { const SnMeta& C = c->h_meta[c->h_child[ci]]; const double uc = C.f - C.k;
+          b += 12.0 * uc * uc * ( double )a.ncols / std::max( 1, P.f ); } }     /* ~ read child + read/write parent over the lower triangle: 24 B x u^2/2, shared by the parent's column tasks */
+      out[i].bytes = b;
+    }
   }
   return n;
 }

@@ -410,6 +410,7 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
     static int starts_env = -1; if ( starts_env < 0 ) { const char* e = getenv( "B200_ND_STARTS" ); starts_env = e ? atoi( e ) : 4; if ( starts_env < 1 ) starts_env = 1; if ( starts_env > 16 ) starts_env = 16; }
     int R = nv >= 1000000 ? 4 * starts_env : nv >= 200000 ? 2 * starts_env : nv >= 30000 ? starts_env : 1;    /* more where a front costs the most */
     if ( R > 16 ) R = 16;
+    if ( starts_env == 1 ) R = 1;          /* B200_ND_STARTS=1: the single-start ordering of mid-round (reproducibility of earlier measurements) */
     int* cand[16]; double score[16];
     for ( int r = 0; r < R; r++ ) cand[r] = r == 0 ? where : malloc( sizeof( int ) * nv );
     for ( int r = 0; r < R; r++ ) {

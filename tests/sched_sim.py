@@ -27,7 +27,7 @@ def export(mc, S, world, rank, with_accesses=False):
     L.b200_debug_schedule(c, le, nl); L.b200_debug_messages(c, me, nm)
     launches = [dict(kind=le[i].kind, stream=le[i].stream, wait=le[i].wait_ev, rec=le[i].record_ev, depth=le[i].depth,
                      msgs=list(range(le[i].first_msg, le[i].first_msg + le[i].nmsg)) if le[i].nmsg > 0 and le[i].first_msg >= 0 else [],
-                     name=L.b200_debug_kind_name(le[i].kind).decode()) for i in range(nl)]
+                     name=L.b200_debug_kind_name(le[i].kind).decode(), count=le[i].count, flops=le[i].flops, kavg=le[i].kavg, bytes=le[i].bytes) for i in range(nl)]
     msgs = [(me[i].src, me[i].dst, me[i].which, me[i].offset, me[i].count) for i in range(nm)]
     if with_accesses:
         import numpy as np
