@@ -421,7 +421,8 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
         long c0 = 0, c1 = 0, c2 = 0;
         for ( int v = 0; v < nv; v++ ) { if ( cand[r][v] == 0 ) c0++; else if ( cand[r][v] == 1 ) c1++; else c2++; }
         const double imb = ( c0 + c1 ) > 0 ? ( double )( c0 > c1 ? c0 - c1 : c1 - c0 ) / ( double )( c0 + c1 ) : 1.0;
-        score[r] = ( c0 == 0 || c1 == 0 ) ? 1e300 : ( double )c2 * ( 1.0 + 2.0 * imb * imb );
+        static double pen = -1.0; if ( pen < 0 ) { const char* e = getenv( "B200_ND_IMB_PENALTY" ); pen = e ? atof( e ) : 2.0; }
+        score[r] = ( c0 == 0 || c1 == 0 ) ? 1e300 : ( double )c2 * ( 1.0 + pen * imb * imb );
       }
     }
     #pragma omp taskwait
