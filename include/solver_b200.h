@@ -43,7 +43,8 @@ enum { B200_OK = 0, B200_ERR_ARG = -1, B200_ERR_NOMEM = -2, B200_ERR_CUDA = -3,
 
 /* factorization kinds */
 enum { B200_KIND_CHOLESKY = 0,   /* P A P' = L L'  (symmetric, upper-CSC input)        */
-       B200_KIND_LU = 1 };       /* P A P' = L U on the pattern of A+A', pivoting in fronts */
+       B200_KIND_LU = 1,         /* P A P' = L U on the pattern of A+A', pivoting in fronts */
+       B200_KIND_LDLT = 2 };     /* P A P' = L D L' (symmetric indefinite, upper-CSC input): 1x1 / 2x2 Bunch-Kaufman pivots inside the fronts */
 
 /* ordering methods for b200_analyze_opts */
 enum { B200_ORDER_ND = 0, B200_ORDER_NATURAL = 1, B200_ORDER_GIVEN = 2 };

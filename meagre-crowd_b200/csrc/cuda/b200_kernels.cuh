@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math_constants.h>
 
 namespace b200 {
 
@@ -91,6 +92,21 @@ __global__ void scatter_A_kernel( const double* __restrict__ vals, const int64_t
     if ( d & ( ( int64_t )1 << 62 ) ) atomicAdd( &U[d & ~( ( int64_t )1 << 62 )], v );
     else atomicAdd( &L[d], v );
   }
+}
+
+/* static-pivot threshold of the LU / LDL' diagonal-block kernels: sqrt(eps) * max|a_ij|, formed on the device so that
+ * values already resident in HBM (b200_factor_device) get the same scaling as host values */
+__global__ void maxabs_kernel( const double* __restrict__ vals, int64_t nnz, unsigned long long* __restrict__ out_bits ) {
+  int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = ( int64_t )gridDim.x * blockDim.x;
+  double m = 0.0;
+  for ( ; e < nnz; e += stride ) { const double a = fabs( vals[e] ); if ( a > m && a < CUDART_INF ) m = a; }
+  for ( int o = 16; o; o >>= 1 ) m = fmax( m, __shfl_xor_sync( 0xffffffffu, m, o ) );
+  if ( ( threadIdx.x & 31 ) == 0 && m > 0.0 ) atomicMax( out_bits, ( unsigned long long )__double_as_longlong( m ) );
+}
+__global__ void tiny_from_max_kernel( const unsigned long long* __restrict__ max_bits, double* __restrict__ tiny ) {
+  const double m = __longlong_as_double( ( long long )*max_bits );
+  *tiny = 1.4901161193847656e-8 * ( m > 0.0 ? m : 1.0 );
 }
 
 /* ------------------------------------------------------------ extend-add
@@ -381,7 +397,8 @@ __global__ void __launch_bounds__( 256 ) small_front_kernel( const int* __restri
  * rows.  piv[j] = block-local row swapped into position j.  Tiny pivots are
  * replaced by +-tiny (static perturbation) and counted.  Outputs: packed L\U
  * in place, inv = inverse of unit-lower L, inv2 = (inverse of U) transposed. */
-__global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __restrict__ tasks, double tiny, int* __restrict__ nperturbed ) {
+__global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed ) {
+  const double tiny = *tiny_p;
   extern __shared__ double dsm[];
   double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
   double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );
@@ -1306,7 +1323,10 @@ __global__ void residual_dd_kernel( const int64_t* __restrict__ rp, const int* _
     }
     const double ri = hi + lo;
     r[e] = ri;
-    if ( den > 0.0 ) omega = fmax( omega, fabs( ri ) / den );
+    /* NaN / Inf anywhere in x must surface as omega = +Inf (fmax would silently drop a NaN) */
+    double w = den > 0.0 ? fabs( ri ) / den : ( ri != 0.0 ? CUDART_INF : 0.0 );
+    if ( !( w == w ) ) w = CUDART_INF;
+    omega = fmax( omega, w );
   }
   for ( int o = 16; o; o >>= 1 ) omega = fmax( omega, __shfl_xor_sync( 0xffffffffu, omega, o ) );
   if ( ( threadIdx.x & 31 ) == 0 && omega > 0.0 ) atomicMax( omega_bits, ( unsigned long long )__double_as_longlong( omega ) );   /* positive doubles order like integers */

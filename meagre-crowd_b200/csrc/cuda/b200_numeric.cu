@@ -127,7 +127,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; bool use_bulk = true, use_pers = false, use_small_front = true; DevVec<int> small_sns; int pers_grid = 444;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; bool use_bulk = true, use_pers = false, use_small_front = true; DevVec<int> small_sns; int pers_grid = 444;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -155,7 +155,6 @@ struct b200_ctx {
   std::vector<GemmTask> h_gt; std::vector<Tile> h_tb; std::vector<DiagTask> h_dt; std::vector<TrsmTask> h_tt; std::vector<RowTile> h_ttl; std::vector<AsmTask> h_at; std::vector<int> h_small, h_child; std::vector<SnMeta> h_meta;
   double prof_ms[LK_COUNT] = { 0 }; int64_t prof_n[LK_COUNT] = { 0 };
   double sprof_ms[SK_COUNT] = { 0 }; int64_t sprof_n[SK_COUNT] = { 0 };
-  double tiny = 0.0;
   b200_stats_t stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evs = nullptr;
   std::vector<cudaEvent_t> lvl_ev; std::vector<float> lvl_ms;   /* update-stream time stamps at level boundaries (diagnostics) */
@@ -175,7 +174,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
     CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); }
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) );
-  CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) );
+  CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_pers_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
@@ -258,9 +257,9 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   if ( !c ) return;
   if ( c->dry ) { release_symbolic( c ); delete c; return; }
   cudaSetDevice( c->device );
-  cudaStreamSynchronize( c->stream );
+  cudaStreamSynchronize( c->stream ); cudaStreamSynchronize( c->stream2 ); cudaStreamSynchronize( c->stream3 ); cudaStreamSynchronize( c->stream4 );   /* pending NCCL sends read dL / dInv */
   release_symbolic( c );
-  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
+  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dTiny ); cudaFree( c->dMaxBits ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
   for ( cudaEvent_t e : c->lvl_ev ) cudaEventDestroy( e );
@@ -678,6 +677,13 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
   }
   if ( MG && ev_bulk_last >= 0 ) { push_nop( 0, 0 ); LS.back().wait_ev = ev_bulk_last; }     /* the factor is complete on this rank once the bulk channel has drained */
+  if ( MG ) { /* ... and once every panel / contribution-block message has left: the sender side of the last broadcasts is otherwise
+               * never joined, and the next factorization would zero L under sends that are still queued */
+    const int e2 = new_event(); push_nop( 0, 2 ); LS.back().record_ev = e2;
+    push_nop( 0, 0 ); LS.back().wait_ev = e2;
+    const int e1 = new_event(); push_nop( 0, 1 ); LS.back().record_ev = e1;
+    push_nop( 0, 0 ); LS.back().wait_ev = e1;
+  }
   if ( c->dry ) { c->h_gt = gt; c->h_tb = tb; c->h_dt = dt; c->h_tt = tt; c->h_ttl = ttl; c->h_at = at; c->h_small = smalls; c->h_child = child_list; c->h_meta = meta; }
   if ( c->small_sns.upload( smalls ) ) return B200_ERR_CUDA;
   if ( c->gemm_tasks.upload( gt ) || c->tiles_big.upload( tb ) || c->tiles_small.upload( ts ) || c->diag_tasks.upload( dt ) ||
@@ -792,6 +798,11 @@ static int run_factor( b200_ctx* c ) {
     const int blocks = ( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 16 );
     scatter_A_kernel<<<blocks, 256, 0, st>>>( c->dVals, c->amap.d, c->nnzA, c->dL, c->dU );
   }
+  if ( LU ) { /* static-pivot threshold sqrt(eps) * max|a_ij| */
+    CK( cudaMemsetAsync( c->dMaxBits, 0, 8, st ) );
+    if ( c->nnzA > 0 ) maxabs_kernel<<<( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 8 ), 256, 0, st>>>( c->dVals, c->nnzA, c->dMaxBits );
+    tiny_from_max_kernel<<<1, 1, 0, st>>>( c->dMaxBits, c->dTiny );
+  }
   if ( c->world > 1 ) { CK( cudaEventRecord( c->evs, st ) ); CK( cudaStreamWaitEvent( c->stream3, c->evs, 0 ) ); CK( cudaStreamWaitEvent( c->stream4, c->evs, 0 ) ); }   /* nothing may land in L before it has been zeroed and scattered */
   int64_t nlaunch = 3 + ( LU ? 1 : 0 );
   double gemm_flops = 0; int64_t gemm_launches = 0;
@@ -812,7 +823,7 @@ static int run_factor( b200_ctx* c ) {
         else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
         break;
       case LK_DIAG:
-        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->tiny, c->dPert );
+        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
         else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
       case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;
@@ -876,7 +887,6 @@ extern "C" int b200_factor_device( b200_ctx_t* c, const double* d_vals ) {
   if ( !c || !c->dL || c->dry ) return B200_ERR_STATE;
   CK( cudaSetDevice( c->device ) );
   if ( d_vals != c->dVals && c->nnzA > 0 ) CK( cudaMemcpyAsync( c->dVals, d_vals, ( size_t )c->nnzA * 8, cudaMemcpyDeviceToDevice, c->stream ) );
-  if ( c->kind == B200_KIND_LU && c->tiny == 0.0 ) c->tiny = 1.5e-8;
   c->stats.h2d_ms = 0;
   return run_factor( c );
 }
@@ -884,10 +894,6 @@ extern "C" int b200_factor_device( b200_ctx_t* c, const double* d_vals ) {
 extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
   if ( !c || !c->dL || c->dry ) return B200_ERR_STATE;
   CK( cudaSetDevice( c->device ) );
-  if ( c->kind == B200_KIND_LU ) { /* static-pivot threshold: sqrt(eps) * max|a_ij| */
-    double mx = 0; for ( int64_t e = 0; e < c->nnzA; e++ ) mx = std::max( mx, std::fabs( vals[e] ) );
-    c->tiny = 1.5e-8 * ( mx > 0 ? mx : 1.0 );
-  }
   CK( cudaEventRecord( c->evp0, c->stream ) );
   if ( c->nnzA > 0 ) CK( cudaMemcpyAsync( c->dVals, vals, ( size_t )c->nnzA * 8, cudaMemcpyHostToDevice, c->stream ) );
   CK( cudaEventRecord( c->evp1, c->stream ) );
@@ -968,13 +974,16 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
   for ( int k = 0; k < SK_COUNT; k++ ) { c->sprof_ms[k] = 0; c->sprof_n[k] = 0; }
   CK( cudaEventRecord( c->ev0, st ) );
   r = sweep_once( c, d_b, p, d_x, nl ); if ( r ) return r;
-  /* iterative refinement with a double-double residual.  Automatic mode: always one step when the
-   * system is small (the extra sweeps cost microseconds and buy the last digits the reference's
-   * known-answer tolerances ask for); otherwise only while the componentwise backward error
-   * max_i |r_i| / (|A||x|+|b|)_i exceeds 1e-15. */
+  /* iterative refinement with a double-double residual.  Automatic mode: the componentwise backward error
+   * omega = max_i |r_i| / (|A||x|+|b|)_i is formed after every pair of sweeps; one correction step always when the
+   * system is small (the extra sweeps cost microseconds and buy the last digits the reference's known-answer
+   * tolerances ask for), otherwise only while omega exceeds 1e-14 -- two orders below the stated 1e-12 bound, so a
+   * well-conditioned SPD system (the headline) runs exactly one pair of sweeps.  omega is NaN-propagating: a
+   * non-finite x ends the solve with B200_ERR_SINGULAR instead of being reported as converged. */
   const int maxit = c->refine >= 0 ? c->refine : 2;
   c->stats.refine_steps = 0; c->stats.backward_error = -1.0; c->stats.first_backward_error = -1.0;
-  for ( int it = 0; it < maxit; it++ ) {
+  for ( int it = 0; it <= maxit; it++ ) {
+    if ( c->refine >= 0 && it == maxit ) break;       /* fixed number of steps: no final residual */
     CK( cudaMemsetAsync( c->dOmega, 0, sizeof( unsigned long long ), st ) );
     residual_dd_kernel<<<pblocks, 256, 0, st>>>( c->spmv_ptr.d, c->spmv_col.d, c->spmv_src.d, c->dVals, d_x, d_b, n, p, c->dR, c->dOmega );
     nl++;
@@ -984,8 +993,9 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
       CK( cudaStreamSynchronize( st ) );
       double omega; memcpy( &omega, &bits, sizeof( omega ) );
       c->stats.backward_error = omega; if ( it == 0 ) c->stats.first_backward_error = omega;
+      if ( !std::isfinite( omega ) ) { set_err( "the solution is not finite (singular or badly pivoted factor)%s", "" ); return B200_ERR_SINGULAR; }
       const bool small = n <= 65536;     /* depends on n only: the answer must not depend on how columns are batched */
-      if ( !( ( small && it == 0 ) || omega > 1e-15 ) ) break;
+      if ( it == maxit || !( ( small && it == 0 ) || omega > 1e-14 ) ) break;
     }
     r = sweep_once( c, c->dR, p, c->dD, nl ); if ( r ) return r;
     axpy_kernel<<<pblocks, 256, 0, st>>>( d_x, c->dD, ( int64_t )n * p );

@@ -28,6 +28,25 @@ typedef struct {
   int* ewgt;
 } graph_t;
 
+/* Tuning knobs from the environment.  Read ONCE in b200_order_nd, before the OpenMP region starts, so that no task
+ * ever sees a half-initialised value: the ordering must not depend on thread timing (ranks of a multi-GPU run derive
+ * their plans from it independently). */
+typedef struct { int fm_cap, tries, fm_big, fm_small, starts, verbose; double ub, pen; } nd_knobs_t;
+static nd_knobs_t g_knobs = { 400, 12, 3, 5, 4, 0, 1.40, 2.0 };
+static void read_knobs( void ) {
+  nd_knobs_t k = { 400, 12, 3, 5, 4, 0, 1.40, 2.0 };
+  const char* e;
+  if ( ( e = getenv( "B200_FM_CAP" ) ) ) k.fm_cap = atoi( e );
+  if ( ( e = getenv( "B200_ND_TRIES" ) ) ) k.tries = atoi( e );
+  if ( ( e = getenv( "B200_FM_PASSES_BIG" ) ) ) k.fm_big = atoi( e );
+  if ( ( e = getenv( "B200_FM_PASSES" ) ) ) k.fm_small = atoi( e );
+  if ( ( e = getenv( "B200_ND_STARTS" ) ) ) { k.starts = atoi( e ); if ( k.starts < 1 ) k.starts = 1; if ( k.starts > 16 ) k.starts = 16; }
+  if ( ( e = getenv( "B200_ND_UB" ) ) ) k.ub = atof( e );
+  if ( ( e = getenv( "B200_ND_IMB_PENALTY" ) ) ) k.pen = atof( e );
+  k.verbose = getenv( "B200_ND_VERBOSE" ) != NULL;
+  g_knobs = k;
+}
+
 static void graph_free( graph_t* g ) {
   if ( !g ) return;
   free( g->xadj ); free( g->adj ); free( g->vwgt ); free( g->ewgt ); free( g );
@@ -156,7 +175,7 @@ static void node_fm( const graph_t* g, int* where, int* pw, int maxpw, int npass
       if ( where[v] == 2 ) { heap_upsert( &H[0], v, sep_gain( g, where, v, 0 ) ); heap_upsert( &H[1], v, sep_gain( g, where, v, 1 ) ); nsepv++; }
     }
     if ( nsepv == 0 ) return;
-    static int fm_cap = -1; if ( fm_cap < 0 ) { const char* e = getenv( "B200_FM_CAP" ); fm_cap = e ? atoi( e ) : 400; }
+    const int fm_cap = g_knobs.fm_cap;
     const int limit = nsepv < 40 ? 40 + nsepv : ( nsepv / 4 + 60 > fm_cap ? fm_cap : nsepv / 4 + 60 );
     int nmoves = 0, npulled = 0, bestmoves = 0;
     int bestsep = pw[2], bestdiff = abs( pw[0] - pw[1] );
@@ -289,7 +308,7 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
     if ( c->nv > 0.93 * G[nl]->nv ) { graph_free( c ); free( cmap ); break; }
     CM[nl] = cmap; G[nl + 1] = c; nl++;
   }
-  static double ub_env = -1.0; if ( ub_env < 0 ) { const char* e = getenv( "B200_ND_UB" ); ub_env = e ? atof( e ) : 1.40; }     /* measured with 4 starts: 1.40 beats 1.20 / 1.30 / 1.50 on 128^3, 96^3, 2-D 1024^2 and 27-pt 64^3 (fill falls when a side may hold up to 70 %) */
+  const double ub_env = g_knobs.ub;     /* default 1.40: measured with 4 starts: 1.40 beats 1.20 / 1.30 / 1.50 on 128^3, 96^3, 2-D 1024^2 and 27-pt 64^3 (fill falls when a side may hold up to 70 %) */
   const double ub = ub_env;
   int maxpw = ( int )( ub * total / 2.0 ) + 1;
   /* initial separators on the coarsest graph */
@@ -304,7 +323,7 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
   heap_t H[2];
   heap_init( &H[0], g0->nv ); heap_init( &H[1], g0->nv );
   long bestscore = -1; int bestpw[3] = {0, 0, 0};
-  static int tries_env = -1; if ( tries_env < 0 ) { const char* e = getenv( "B200_ND_TRIES" ); tries_env = e ? atoi( e ) : 12; }
+  const int tries_env = g_knobs.tries;
   int ntries = cnv < tries_env ? cnv : tries_env;
   for ( int t = 0; t < ntries; t++ ) {
     int seed = rng_next( rng ) % ( uint32_t )cnv;
@@ -323,7 +342,7 @@ static void multilevel_separator( graph_t* g0, int* where0, uint32_t* rng ) {
     for ( int v = 0; v < gf->nv; v++ ) wf[v] = cur[CM[l][v]];
     free( cur ); cur = wf;
     /* projected separators are thick: vertices with no neighbour on one side can leave for free */
-    static int fm_big = -1, fm_small = -1; if ( fm_big < 0 ) { const char* e = getenv( "B200_FM_PASSES_BIG" ); fm_big = e ? atoi( e ) : 3; e = getenv( "B200_FM_PASSES" ); fm_small = e ? atoi( e ) : 5; }
+    const int fm_big = g_knobs.fm_big, fm_small = g_knobs.fm_small;
     node_fm( gf, cur, pw, maxpw, gf->nv > 200000 ? fm_big : fm_small, H, locked, pulled, moves );
     graph_free( G[l + 1] ); free( CM[l] );
   }
@@ -407,7 +426,7 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
      * top of the recursion has idle cores anyway (1, 2, 4 ... subgraphs), so R independent runs with different
      * seeds go out as tasks and the smallest separator (with a mild imbalance penalty) wins; ties go to the
      * lower run index, so the result does not depend on the number of threads. */
-    static int starts_env = -1; if ( starts_env < 0 ) { const char* e = getenv( "B200_ND_STARTS" ); starts_env = e ? atoi( e ) : 4; if ( starts_env < 1 ) starts_env = 1; if ( starts_env > 16 ) starts_env = 16; }
+    const int starts_env = g_knobs.starts;
     int R = nv >= 1000000 ? 4 * starts_env : nv >= 200000 ? 2 * starts_env : nv >= 30000 ? starts_env : 1;    /* more where a front costs the most */
     if ( R > 16 ) R = 16;
     if ( starts_env == 1 ) R = 1;          /* B200_ND_STARTS=1: the single-start ordering of mid-round (reproducibility of earlier measurements) */
@@ -421,7 +440,7 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
         long c0 = 0, c1 = 0, c2 = 0;
         for ( int v = 0; v < nv; v++ ) { if ( cand[r][v] == 0 ) c0++; else if ( cand[r][v] == 1 ) c1++; else c2++; }
         const double imb = ( c0 + c1 ) > 0 ? ( double )( c0 > c1 ? c0 - c1 : c1 - c0 ) / ( double )( c0 + c1 ) : 1.0;
-        static double pen = -1.0; if ( pen < 0 ) { const char* e = getenv( "B200_ND_IMB_PENALTY" ); pen = e ? atof( e ) : 2.0; }
+        const double pen = g_knobs.pen;
         score[r] = ( c0 == 0 || c1 == 0 ) ? 1e300 : ( double )c2 * ( 1.0 + pen * imb * imb );
       }
     }
@@ -432,7 +451,7 @@ static void nd_rec( graph_t* g, int* label, int* perm, int first, int leaf, int 
     for ( int r = 1; r < R; r++ ) free( cand[r] );
   }
   for ( int v = 0; v < nv; v++ ) { if ( where[v] == 0 ) n0++; else if ( where[v] == 1 ) n1++; else n2++; }
-  { static int verbose = -1; if ( verbose < 0 ) verbose = getenv( "B200_ND_VERBOSE" ) != NULL; if ( verbose && nv >= 20000 ) fprintf( stderr, "nd depth %d: nv=%d -> %d | %d | sep %d\n", depth, nv, n0, n1, n2 ); }
+  { const int verbose = g_knobs.verbose; if ( verbose && nv >= 20000 ) fprintf( stderr, "nd depth %d: nv=%d -> %d | %d | sep %d\n", depth, nv, n0, n1, n2 ); }
   if ( n0 == 0 || n1 == 0 ) {
     /* bisection failed (e.g. a clique): order what is left by degree-sorted natural order in chunks */
     if ( nv <= 4096 ) {
@@ -476,6 +495,7 @@ int b200_order_nd( int n, const int* xadj, const int* adj, int leaf, int threads
   for ( int i = 0; i < g->ne; i++ ) g->ewgt[i] = 1;
   int* label = malloc( sizeof( int ) * n );
   for ( int i = 0; i < n; i++ ) label[i] = i;
+  read_knobs();
 #ifdef _OPENMP
   int nt = threads > 0 ? threads : omp_get_max_threads();
   #pragma omp parallel num_threads(nt)

@@ -143,7 +143,7 @@ static int build_lower_pattern( int n, const unsigned int* cp, const unsigned in
     for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
       int i = ( int )ri[p];
       if ( i == j ) continue;
-      if ( kind == B200_KIND_CHOLESKY && i > j ) continue;
+      if ( kind != B200_KIND_LU && i > j ) continue;
       int a = iperm[i], b = iperm[j];
       int c = a < b ? a : b;
       cnt[c + 1]++;
@@ -157,7 +157,7 @@ static int build_lower_pattern( int n, const unsigned int* cp, const unsigned in
     for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
       int i = ( int )ri[p];
       if ( i == j ) continue;
-      if ( kind == B200_KIND_CHOLESKY && i > j ) continue;
+      if ( kind != B200_KIND_LU && i > j ) continue;
       int a = iperm[i], b = iperm[j];
       int c = a < b ? a : b, r = a < b ? b : a;
       li[cnt[c]++] = r;
@@ -200,8 +200,12 @@ static inline double panel_flops( double k, double f ) { /* sum_{j<k} (f-j)^2 */
 b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int* ri, int kind, const b200_options_t* opts_in ) {
   b200_options_t opts;
   if ( opts_in ) opts = *opts_in; else b200_default_options( &opts );
-  if ( n <= 0 || !cp || ( kind != B200_KIND_CHOLESKY && kind != B200_KIND_LU ) ) return NULL;
+  if ( n <= 0 || !cp || ( kind != B200_KIND_CHOLESKY && kind != B200_KIND_LU && kind != B200_KIND_LDLT ) ) return NULL;
   if ( ( uint64_t )cp[n] > 0x7fffffffu ) return NULL;
+  /* a malformed caller must end here, not in an out-of-bounds write on the host or the device */
+  if ( cp[0] != 0 || ( cp[n] > 0 && !ri ) ) { fprintf( stderr, "b200_analyze: bad column pointers\n" ); return NULL; }
+  for ( int j = 0; j < n; j++ ) if ( cp[j + 1] < cp[j] ) { fprintf( stderr, "b200_analyze: column pointers are not monotone (column %d)\n", j ); return NULL; }
+  for ( unsigned int p = 0; p < cp[n]; p++ ) if ( ri[p] >= ( unsigned int )n ) { fprintf( stderr, "b200_analyze: row index %u out of range at entry %u\n", ri[p], p ); return NULL; }
   double t0 = now_s();
   b200_symbolic_t* S = calloc( 1, sizeof( *S ) );
   S->n = n; S->kind = kind; S->nnzA = cp[n];
@@ -427,12 +431,12 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
     int64_t k = sn_start[s + 1] - sn_start[s], f = S->rowptr[s + 1] - S->rowptr[s], u = f - k;
     const int64_t ld = ( f + 1 ) & ~( int64_t )1, ldu = ( u + 1 ) & ~( int64_t )1;   /* even leading dimensions: 16-byte aligned columns */
     S->lptr[s] = lo; lo += ld * k;
-    S->uptr[s] = ( kind == B200_KIND_LU ) ? S->lptr[s] : 0; ( void )uo;
+    S->uptr[s] = ( kind != B200_KIND_CHOLESKY ) ? S->lptr[s] : 0; ( void )uo;
     sf += panel_flops( ( double )k, ( double )f );
     int d = S->sn_depth[s];
     S->cbptr[s] = dsum[d]; dsum[d] += ldu * u;
   }
-  S->lptr[ns] = lo; S->uptr[ns] = ( kind == B200_KIND_LU ) ? lo : 0; S->stored_nnzL = lo; S->stored_flops = sf;
+  S->lptr[ns] = lo; S->uptr[ns] = ( kind != B200_KIND_CHOLESKY ) ? lo : 0; S->stored_nnzL = lo; S->stored_flops = sf;
   S->cb_arena[0] = S->cb_arena[1] = 0;
   for ( int d = 0; d <= maxdepth; d++ ) if ( dsum[d] > S->cb_arena[d & 1] ) S->cb_arena[d & 1] = dsum[d];
   free( dsum );
@@ -458,10 +462,10 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
   for ( int j = 0; j < n; j++ ) {
     for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
       int i = ( int )ri[p];
-      if ( kind == B200_KIND_CHOLESKY && i > j ) { S->amap[p] = -1; continue; }
+      if ( kind != B200_KIND_LU && i > j ) { S->amap[p] = -1; continue; }
       int pr = S->iperm[i], pc = S->iperm[j];   /* entry A(i,j) -> (pr,pc) of the permuted matrix */
       int r, c, upper = 0;
-      if ( kind == B200_KIND_CHOLESKY ) { r = pr > pc ? pr : pc; c = pr > pc ? pc : pr; }
+      if ( kind != B200_KIND_LU ) { r = pr > pc ? pr : pc; c = pr > pc ? pc : pr; }
       else if ( pr >= pc ) { r = pr; c = pc; }
       else { r = pc; c = pr; upper = 1; }        /* U(pr,pc): row pr belongs to supernode of pr */
       int s = col2sn[c];
@@ -489,7 +493,7 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
     for ( int j = 0; j < n; j++ )
       for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
         int i = ( int )ri[p];
-        if ( kind == B200_KIND_CHOLESKY ) { if ( i > j ) continue; rp[i + 1]++; if ( i != j ) rp[j + 1]++; }
+        if ( kind != B200_KIND_LU ) { if ( i > j ) continue; rp[i + 1]++; if ( i != j ) rp[j + 1]++; }
         else rp[i + 1]++;
       }
     for ( int i = 0; i < n; i++ ) rp[i + 1] += rp[i];
@@ -498,9 +502,9 @@ b200_symbolic_t* b200_analyze( int n, const unsigned int* cp, const unsigned int
     for ( int j = 0; j < n; j++ )
       for ( unsigned int p = cp[j]; p < cp[j + 1]; p++ ) {
         int i = ( int )ri[p];
-        if ( kind == B200_KIND_CHOLESKY && i > j ) continue;
+        if ( kind != B200_KIND_LU && i > j ) continue;
         int64_t q = w[i]++; S->spmv_col[q] = j; S->spmv_src[q] = ( int )p;
-        if ( kind == B200_KIND_CHOLESKY && i != j ) { q = w[j]++; S->spmv_col[q] = i; S->spmv_src[q] = ( int )p; }
+        if ( kind != B200_KIND_LU && i != j ) { q = w[j]++; S->spmv_col[q] = i; S->spmv_src[q] = ( int )p; }
       }
     free( w );
     S->spmv_ptr = rp;

@@ -9,6 +9,8 @@
  * "general" files go through detect_matrix_symmetry (src/file.c:664-665).
  */
 #include <stdio.h>
+#include <limits.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
@@ -78,8 +80,12 @@ static int readmm( const char* filename, matrix_t* A ) {
     const char* p = line;
     if ( tok_uint( &p, &rows ) || tok_uint( &p, &cols ) ) { fclose( f ); return -12; }
     if ( coord ) { if ( tok_uint( &p, &nz ) ) { fclose( f ); return -12; } }
-    else nz = rows * cols;
+    else {
+      if ( rows > 0 && cols > LONG_MAX / rows ) { fclose( f ); return -12; }     /* rows*cols must not wrap */
+      nz = rows * cols;
+    }
     if ( !rest_blank( p ) ) { fclose( f ); return -12; }
+    if ( rows > ( long )UINT_MAX || cols > ( long )UINT_MAX || ( unsigned long )nz > SIZE_MAX / sizeof( double ) ) { fclose( f ); return -12; }
     break;
   }
   clear_matrix( A );
@@ -89,16 +95,19 @@ static int readmm( const char* filename, matrix_t* A ) {
   A->data_type = REAL_DOUBLE;
   A->sym = sym;
   double* dd = malloc( sizeof( double ) * ( nz ? nz : 1 ) );
+  if ( dd == NULL ) { fclose( f ); clear_matrix( A ); return -12; }
   int ret = 0;
   if ( coord ) {
     A->format = SM_COO;
     unsigned int* ii = malloc( sizeof( unsigned int ) * ( nz ? nz : 1 ) );
     unsigned int* jj = malloc( sizeof( unsigned int ) * ( nz ? nz : 1 ) );
+    if ( ii == NULL || jj == NULL ) { free( ii ); free( jj ); free( dd ); fclose( f ); clear_matrix( A ); return -12; }
     for ( long k = 0; k < nz; k++ ) {
       if ( fgets( line, sizeof( line ), f ) == NULL ) { ret = -11; break; }
       if ( strlen( line ) > MM_LINE_MAX ) { ret = -13; break; }
       const char* p = line; long i, j; double v;
       if ( tok_uint( &p, &i ) || tok_uint( &p, &j ) || tok_real( &p, &v ) || !rest_blank( p ) ) { ret = -12; break; }
+      if ( i < 1 || i > rows || j < 1 || j > cols ) { ret = -12; break; }     /* 1-based indices inside the declared size (the reference leaves this as a TODO) */
       ii[k] = ( unsigned int )i; jj[k] = ( unsigned int )j; dd[k] = v;
     }
     A->ii = ii; A->jj = jj;

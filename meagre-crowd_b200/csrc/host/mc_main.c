@@ -120,9 +120,10 @@ int main( int argc, char** argv ) {
   if ( args->verbosity >= 1 ) {
     int ierr = convert_matrix( A, SM_COO, FIRST_INDEX_ZERO ); assert( ierr == 0 ); ( void )ierr;
     const char* sym = A->sym == SM_UNSYMMETRIC ? "unsymmetric" : A->sym == SM_SYMMETRIC ? "symmetric" : A->sym == SM_SKEW_SYMMETRIC ? "skew symmetric" : "hermitian";
-    const char* loc = A->sym == SM_UNSYMMETRIC ? "" : A->location == UPPER_TRIANGULAR ? " (upper)" : A->location == LOWER_TRIANGULAR ? " (lower)" : " (both)";
+    /* src/meagre-crowd.c:277-295: the storage suffix only at -vv, never for MC_STORE_BOTH */
+    const char* loc = ( args->verbosity < 2 || A->sym == SM_UNSYMMETRIC ) ? "" : A->location == UPPER_TRIANGULAR ? " (upper)" : A->location == LOWER_TRIANGULAR ? " (lower)" : "";
     printf( "Ax=b: A is %zux%zu, nz=%zu, %s%s, %s, b is %zux%zu, nz=%zu\nsolved with %s on %d core%s, %d thread%s\n",
-            A->m, A->n, A->nz, sym, loc, "real double", b->m, b->n, b->nz, solver2str( args->solver ), c_mpi, c_mpi == 1 ? "" : "s", c_omp, c_omp == 1 ? "" : "s" );
+            A->m, A->n, A->nz, sym, loc, "real", b->m, b->n, b->nz, solver2str( args->solver ), c_mpi, c_mpi == 1 ? "" : "s", c_omp, c_omp == 1 ? "" : "s" );
     if ( args->verbosity >= 2 ) { printf_matrix( "  A", A ); printf_matrix( "  b", b ); }
   }
 

@@ -148,6 +148,14 @@ void solver_evaluate_b200( solver_state_t* s, matrix_t* b, matrix_t* x ) {
   double* xd = malloc( sizeof( double ) * p->n * ( np ? np : 1 ) );   /* ownership passes to the caller */
   assert( xd != NULL );
   if ( b200_solve_host( p->ctx, b->dd, ( int )np, xd ) != B200_OK ) die( "solve failed" );
+  { /* statically perturbed pivots are only acceptable if refinement recovered a backward-stable answer: the reference
+     * aborts on a singular factorization (assert( status == UMFPACK_OK ), src/solver_umfpack.c:98-101) */
+    b200_stats_t st;
+    if ( b200_get_stats( p->ctx, &st ) == B200_OK && st.npiv_perturbed > 0 ) {
+      if ( st.backward_error > 1e-8 ) { fprintf( stderr, "b200 solver: %d perturbed pivots and componentwise backward error %.2e after refinement: matrix is numerically singular\n", st.npiv_perturbed, st.backward_error ); abort(); }
+      if ( s->verbosity >= 1 ) fprintf( stderr, "b200 solver: warning: %d pivots were perturbed; backward error after %d refinement steps %.2e\n", st.npiv_perturbed, st.refine_steps, st.backward_error );
+    }
+  }
   clear_matrix( x );
   x->m = p->n; x->n = np; x->nz = p->n * np;
   x->format = DCOL; x->base = FIRST_INDEX_ZERO; x->sym = SM_UNSYMMETRIC; x->location = MC_STORE_BOTH; x->data_type = REAL_DOUBLE;

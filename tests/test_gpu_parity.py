@@ -86,7 +86,7 @@ def test_cli_output_formats(mc, golden, tmp_path):
     assert r.stdout.splitlines()[1].endswith("analyze, factorize, evaluate, done, total (ms)")     # the extra "test" tic (src/meagre-crowd.c:370)
     assert subprocess.run([mc.CLI_PATH, "-i", u, "-t", "-r", "3"], capture_output=True, text=True).returncode == 0
     r = subprocess.run([mc.CLI_PATH, "-i", u, "-v"], capture_output=True, text=True)
-    assert r.stdout.startswith("Ax=b: A is 5x5, nz=11, unsymmetric, real double, b is 5x1, nz=5\nsolved with B200-multifrontal on 0 cores, 0 threads\n")
+    assert r.stdout.startswith("Ax=b: A is 5x5, nz=11, unsymmetric, real, b is 5x1, nz=5\nsolved with B200-multifrontal on 0 cores, 0 threads\n")
     for flags in ("-vv", "-vvv", "-tt", "-ttt", "-tttt"):
         assert subprocess.run([mc.CLI_PATH, "-i", u, flags], capture_output=True, text=True).returncode == 0
 
