@@ -180,7 +180,8 @@ int b200_mg_rank( b200_ctx_t* c, int* rank, int* world );
 /* iterative refinement: r = b - A x is accumulated in double-double on the device, then one more
  * pair of sweeps corrects x.  steps >= 0: exactly that many; steps < 0 (default): automatic -- one
  * step for small systems (n <= 65536), otherwise only while the componentwise backward error
- * max_i |r_i| / (|A||x|+|b|)_i is above 1e-15 (at most 2 steps) */
+ * max_i |r_i| / (|A||x|+|b|)_i is above 1e-14 (at most 2 steps); in automatic mode the last residual is always formed on the
+ * FINAL x, its backward error is reported in b200_stats_t.backward_error, and a non-finite x fails with B200_ERR_SINGULAR */
 int b200_set_refinement( b200_ctx_t* c, int steps );
 
 /* statistics of the last factor / solve (device-event milliseconds) */
@@ -219,6 +220,10 @@ int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t cap );
 const char* b200_debug_kind_name( int kind );
 typedef struct b200_access { int launch, which, write; int64_t offset, count; } b200_access_t;   /* conservative interval a compute launch reads (0) or writes (1) */
 int64_t b200_debug_accesses( b200_ctx_t* c, b200_access_t* out, int64_t cap );
+
+/* checksum of the factor: colsq[j] = sum_i L(i,j)^2 over the stored rows of column j (permuted numbering), n doubles on the host;
+ * fixed reduction order, so identical factors give identical bits (Cholesky: the total equals trace(A)) */
+int b200_factor_colnorms( b200_ctx_t* c, double* colsq );
 
 /* diagnostics for the parity tests: read back factor storage (0 = L panels, 1 = U' panels, 2 = inverse blocks) */
 int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int64_t count );

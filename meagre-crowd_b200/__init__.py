@@ -26,7 +26,7 @@ SM_UNSYMMETRIC, SM_SYMMETRIC, SM_SKEW_SYMMETRIC, SM_HERMITIAN = range(4)
 MC_STORE_BOTH, UPPER_TRIANGULAR, LOWER_TRIANGULAR = range(3)
 REAL_DOUBLE = 0
 B200_OK, B200_ERR_ARG, B200_ERR_NOMEM, B200_ERR_CUDA, B200_ERR_NOT_SPD, B200_ERR_SINGULAR, B200_ERR_STATE = 0, -1, -2, -3, -4, -5, -6
-KIND_CHOLESKY, KIND_LU = 0, 1
+KIND_CHOLESKY, KIND_LU, KIND_LDLT = 0, 1, 2
 ORDER_ND, ORDER_NATURAL, ORDER_GIVEN = 0, 1, 2
 
 
@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
     "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dgemm_variant", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
     "b200_outer_width", "b200_set_outer_width_cap", "b200_plan_create", "b200_plan_free", "b200_plan_col_owner", "b200_plan_member", "b200_plan_cb_transfers",
-    "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank", "b200_bench_potrf_us", "b200_bench_dgemm_bulk_variant", "b200_ctx_create_dry", "b200_debug_schedule", "b200_debug_messages", "b200_debug_kind_name", "b200_debug_accesses",
+    "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank", "b200_bench_potrf_us", "b200_bench_dgemm_bulk_variant", "b200_ctx_create_dry", "b200_debug_schedule", "b200_debug_messages", "b200_debug_kind_name", "b200_debug_accesses", "b200_factor_colnorms",
 ]
 
 _lib = None
@@ -188,6 +188,7 @@ def lib():
     L.b200_get_profile.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.b200_set_refinement.argtypes = [vp, i32]
     L.b200_debug_read.argtypes = [vp, i32, vp, i64, i64]
+    L.b200_factor_colnorms.argtypes = [vp, vp]
     L.b200_bench_potrf_us.restype = dbl; L.b200_bench_potrf_us.argtypes = [vp, i32, i32, i32, i32]
     L.b200_bench_dgemm_bulk_variant.restype = dbl; L.b200_bench_dgemm_bulk_variant.argtypes = [vp, i32, i32, i32, i32, i32]
     L.b200_bench_dgemm_tflops.restype = dbl; L.b200_bench_dgemm_tflops.argtypes = [vp, i32, i32, i32, i32]
@@ -383,6 +384,14 @@ class Solver:
             panel = panel_view(flat, lp[s], f, k)
             Ld[np.ix_(rows, np.arange(st[s], st[s + 1]))] = panel
         return np.tril(Ld)
+
+    def colnorms(self):
+        """per-column sums of squares of L (permuted numbering); deterministic checksum of the factor"""
+        out = np.empty(self.n, dtype=np.float64)
+        r = self.L.b200_factor_colnorms(self.ctx, out.ctypes.data)
+        if r != B200_OK:
+            raise RuntimeError("b200_factor_colnorms: " + self.err())
+        return out
 
     def stats(self):
         st = b200_stats_t()

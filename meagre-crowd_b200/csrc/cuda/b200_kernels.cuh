@@ -1337,6 +1337,23 @@ __global__ void axpy_kernel( double* __restrict__ x, const double* __restrict__ 
   for ( ; e < tot; e += stride ) x[e] += d[e];
 }
 
+/* checksum of the factor: out[c0 + j] = sum of squares of the stored entries of column j of the supernode's panel (rows >= j),
+ * one CTA per supernode, one warp per column, lanes stride the rows and are joined by a fixed shuffle tree -- the same bits
+ * whatever the launch geometry.  Cholesky: the sum over all columns equals trace(A). */
+__global__ void __launch_bounds__( 256 ) panel_colnorm_kernel( const SnMeta* __restrict__ sn, int ns, const double* __restrict__ L, double* __restrict__ out ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for ( int s = blockIdx.x; s < ns; s += gridDim.x ) {
+    const SnMeta S = sn[s];
+    for ( int j = warp; j < S.k; j += 8 ) {
+      const double* col = L + S.lptr + ( int64_t )j * S.ld;
+      double acc = 0.0;
+      for ( int i = j + lane; i < S.f; i += 32 ) acc += col[i] * col[i];
+      for ( int o = 16; o; o >>= 1 ) acc += __shfl_xor_sync( 0xffffffffu, acc, o );
+      if ( lane == 0 ) out[S.c0 + j] = acc;
+    }
+  }
+}
+
 /* micro-benchmark: issue-rate roof of DMMA.8x8x4 (registers only, 16 independent accumulators per warp) */
 __global__ void __launch_bounds__( 256 ) dmma_peak_kernel( double* out, int iters ) {
   double acc[16][2];

@@ -858,7 +858,7 @@ static int run_factor( b200_ctx* c ) {
       float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->prof_ms[l.kind] += ms; c->prof_n[l.kind]++;
       static const bool trace = getenv( "B200_TRACE_GEMM" ) != nullptr;
       static const bool trace_all = getenv( "B200_TRACE_ALL" ) != nullptr;
-      if ( trace_all ) fprintf( stderr, "launch %s depth=%d count=%lld stream=%d ms=%.4f\n", kind_name[l.kind], l.depth, ( long long )l.count, l.stream, ms );
+      if ( trace_all ) fprintf( stderr, "launch %s depth=%d count=%lld stream=%d ms=%.4f flops=%.4e\n", kind_name[l.kind], l.depth, ( long long )l.count, l.stream, ms, l.flops );
       if ( trace && l.kind == LK_GEMM_BIG && ms > 0.5f )
         fprintf( stderr, "gemm depth=%d tiles=%lld flops=%.3e ms=%.3f TF/s=%.2f\n", l.depth, ( long long )l.count, l.flops, ms, l.flops / ( ms * 1e-3 ) / 1e12 );
     }
@@ -959,6 +959,8 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
     if ( c->profile ) {
       CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) );
       float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->sprof_ms[l.kind] += ms; c->sprof_n[l.kind]++;
+      static const bool trace_all = getenv( "B200_TRACE_ALL" ) != nullptr;
+      if ( trace_all ) fprintf( stderr, "slaunch kind=%d depth=%d blocks=%lld tiles=%lld ms=%.4f\n", l.kind, l.depth, ( long long )l.count, ( long long )l.ntiles, ms );
     }
   }
   permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dZ, c->perm.d, n, p, d_x );
@@ -1058,7 +1060,7 @@ extern "C" int b200_flush_l2( b200_ctx_t* c ) {
   return B200_OK;
 }
 extern "C" int b200_get_stats( b200_ctx_t* c, b200_stats_t* out ) { if ( !c || !out ) return B200_ERR_ARG; *out = c->stats; return B200_OK; }
-extern "C" int b200_set_refinement( b200_ctx_t* c, int steps ) { if ( !c || steps < 0 ) return B200_ERR_ARG; c->refine = steps; return B200_OK; }
+extern "C" int b200_set_refinement( b200_ctx_t* c, int steps ) { if ( !c ) return B200_ERR_ARG; c->refine = steps < 0 ? -1 : steps; return B200_OK; }
 extern "C" int b200_set_profile( b200_ctx_t* c, int on ) { if ( !c ) return B200_ERR_ARG; c->profile = on != 0; return B200_OK; }
 extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   if ( !c || !buf || len == 0 ) return B200_ERR_ARG;
@@ -1080,6 +1082,20 @@ extern "C" int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t o
   const double* src = which == 0 ? c->dL : which == 1 ? c->dU : which == 2 ? c->dInv : which == 3 ? c->dSinvF : c->dSinvB;
   if ( !src ) return B200_ERR_STATE;
   CK( cudaMemcpy( dst, src + offset, ( size_t )count * 8, cudaMemcpyDeviceToHost ) );
+  return B200_OK;
+}
+
+/* checksum of the factor held by this context: colsq[j] = sum of squares of column j of L (permuted numbering), n doubles on the host.
+ * Deterministic (fixed reduction order), so equal factors give equal bits on any number of GPUs. */
+extern "C" int b200_factor_colnorms( b200_ctx_t* c, double* colsq ) {
+  if ( !c || !colsq || !c->factored || c->dry ) return B200_ERR_STATE;
+  CK( cudaSetDevice( c->device ) );
+  double* d = nullptr; CK( cudaMalloc( &d, ( size_t )c->n * 8 ) );
+  CK( cudaMemsetAsync( d, 0, ( size_t )c->n * 8, c->stream ) );
+  panel_colnorm_kernel<<<148 * 8, 256, 0, c->stream>>>( c->sn.d, c->ns, c->dL, d );
+  CK( cudaMemcpyAsync( colsq, d, ( size_t )c->n * 8, cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  cudaFree( d );
   return B200_OK;
 }
 

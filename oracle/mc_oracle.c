@@ -242,7 +242,7 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
   for ( int d = maxdepth; d >= 0 && !err; d-- ) {
     const int cnt = lcnt[d + 1] - lcnt[d];
     /* many fronts: one thread each with a serial BLAS; few fronts: serial loop with a threaded BLAS */
-    const int par = cnt >= 2 * threads;
+    const int par = 2 * cnt >= threads;
     if ( f_setthr ) f_setthr( par ? 1 : threads );
     #pragma omp parallel for schedule(dynamic,1) num_threads(threads) if(par)
     for ( int t = 0; t < cnt; t++ ) {
@@ -250,7 +250,12 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
       const int c0 = sn_start[s], k = sn_start[s + 1] - c0;
       const int f = ( int )( rowptr[s + 1] - rowptr[s] ), u = f - k;
       const int* rows = rowidx + rowptr[s];
-      double* F = calloc( ( size_t )f * f, sizeof( double ) );
+      /* big fronts (serial loop over the level, threaded BLAS): zero-fill, extend-add and copy-out are spread over the
+       * threads as well -- left serial they, not the BLAS-3 calls, bound the top of the tree on many cores */
+      const int inner = par ? 1 : threads;
+      double* F = malloc( ( size_t )f * f * sizeof( double ) );
+      #pragma omp parallel for schedule(static) num_threads(inner) if(inner > 1 && f >= 512)
+      for ( int j = 0; j < f; j++ ) memset( F + ( size_t )j * f, 0, sizeof( double ) * f );
       int* pos = malloc( sizeof( int ) * f );  /* binary search helper not needed: build a local map via sorted rows */
       /* assemble A */
       for ( int64_t q = acnt[s]; q < acnt[s + 1]; q++ ) {
@@ -268,6 +273,7 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
         int a = 0;
         for ( int i = 0; i < uc; i++ ) { while ( rows[a] != rc[i] ) a++; rel[i] = a; }
         const double* C = cb[c];
+        #pragma omp parallel for schedule(dynamic,16) num_threads(inner) if(inner > 1 && uc >= 512)
         for ( int j = 0; j < uc; j++ ) { double* dst = F + ( size_t )rel[j] * f; const double* src = C + ( size_t )j * uc; for ( int i = j; i < uc; i++ ) dst[rel[i]] += src[i]; }
         free( rel ); free( cb[c] ); cb[c] = NULL;
       }
@@ -279,9 +285,11 @@ int oracle_mf_cholesky( int n, const int* cp, const int* ri, const double* vx, c
       /* keep the panel, pass the contribution block up */
       double* P = Lpanels + lptr[s];
       const size_t ld = ( ( size_t )f + 1 ) & ~( size_t )1;   /* panels use an even leading dimension */
+      #pragma omp parallel for schedule(static) num_threads(inner) if(inner > 1 && f >= 512)
       for ( int j = 0; j < k; j++ ) { memcpy( P + ( size_t )j * ld + j, F + ( size_t )j * f + j, sizeof( double ) * ( f - j ) ); for ( int i = 0; i < j; i++ ) P[( size_t )j * ld + i] = 0.0; }
       if ( u > 0 ) {
         double* C = malloc( sizeof( double ) * ( size_t )u * u );
+        #pragma omp parallel for schedule(static) num_threads(inner) if(inner > 1 && u >= 512)
         for ( int j = 0; j < u; j++ ) memcpy( C + ( size_t )j * u, F + ( size_t )( k + j ) * f + k, sizeof( double ) * u );
         cb[s] = C;
       }
