@@ -59,7 +59,8 @@ struct SnMeta {           /* per supernode, device copy */
   int64_t lptr, uptr, cbptr, rowptr, invptr;
   int c0, k, f, parent, depth, child_begin, child_end, ld;   /* ld: leading dimension of the panel (f rounded up to even) */
   int64_t wptr;           /* solve workspace row offset within its level arena */
-  int64_t sinv;           /* offset of its solve-block inverses (ceil(k/SB) blocks, nb x nb each) */
+  int64_t sinv;           /* offset of its solve-block inverses: block t at sinv + t * sbw^2, leading dimension = width rounded up to even */
+  int sbw;                /* solve block width: SB, or SB_WIDE for the big fronts */
 };
 
 
@@ -893,18 +894,45 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt
   }
 }
 
-/* -------------------------------------------------------------- solves */
-constexpr int PC = 8;   /* right-hand sides per pass */
+/* -------------------------------------------------------------- solves
+ * Level-set sweeps over supernodes.  A supernode's k pivot columns are cut into SOLVE BLOCKS of sbw columns (256, or SB_WIDE
+ * for the big fronts at the top of the tree); for every block the factorization leaves behind the explicit inverse of its
+ * triangular diagonal block (build_sinv_kernel), so a sweep is a sequence of dense products per block b:
+ *     forward :  z_b = X_b y_b ;            y[rows below b] -= L[rows below b, b] z_b
+ *     backward:  x_b = X_b' (z_b - ...) ;   z[cols before b] -= L[b, cols before]' x_b     (update rows first, x gathered from the ancestors)
+ * Every product is an SvTask "dest (-)= M v".  Two implementations execute the same task lists:
+ *     p <= 4 right-hand sides : FMA kernels below (sv_gemv_kernel: outputs = rows of M; sv_gemvT_kernel: outputs = columns of M) -- HBM bound
+ *     p >= 5                  : the FP64 tensor pipe, gemm_solve_dmma_kernel, with the right-hand sides as the M dimension of a DMMA tile
+ * Both follow ONE canonical arithmetic, so that a column's bits do not depend on how many columns travel with it:
+ *     the reduction index k is cut into chunks of KC = 64; inside a chunk the sum is an FMA chain from 0 in ascending k
+ *     (measured: DMMA.8x8x4 is bit-identical to that chain, scripts/probe/dmma_order.cu); the chunk sums p_0, p_1, ... are then
+ *     subtracted one after the other:  dest = ((dest - p_0) - p_1) - ...   (mode 1: dest = -(((0 - p_0) - p_1) - ...)).
+ * Vectors are stored with the right-hand sides contiguous: element (row, q) at row * pitch + q. */
+constexpr int KC = 64;          /* canonical chunk of the reduction index */
+constexpr int SB = 256;         /* solve block width of ordinary supernodes */
+constexpr int SB_WIDE = 1024;   /* ... of supernodes with at least SB_WIDE_MIN pivot columns */
+constexpr int SB_WIDE_MIN = 2048;
 
-__global__ void permute_in_kernel( const double* __restrict__ b, const int* __restrict__ perm, int n, int p, double* __restrict__ y ) {
+struct SvTask {
+  const double* M; int ld;      /* slab of the factor (or of a block inverse), column-major                                        */
+  int K, N;                     /* reduction length, number of outputs.  gemv: M is N x K, outputs = rows; gemvT: M is K x N        */
+  int tri;                      /* gemv: 0 dense, 1 lower triangular (output r uses k <= r), 2 upper triangular (k >= r)            */
+  int mode;                     /* 0: dest -= M v ; 1: dest = M v                                                                   */
+  int vsel, dsel;               /* vector bases: 0 Y, 1 Z, 2 W[0], 3 W[1]                                                           */
+  int64_t voff, doff;           /* first row of v (K rows) and of dest (N rows) inside their base                                   */
+};
+struct SvTile { int task; int o0; };
+struct SvBases { double* b[4]; };
+
+__global__ void permute_in_kernel( const double* __restrict__ b, const int* __restrict__ perm, int n, int p, int pitch, double* __restrict__ y ) {
   int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
-  for ( ; e < tot; e += stride ) { int k = ( int )( e % n ); int64_t c = e / n; y[e] = b[perm[k] + c * n]; }
+  const int64_t tot = ( int64_t )n * pitch, stride = ( int64_t )gridDim.x * blockDim.x;
+  for ( ; e < tot; e += stride ) { const int q = ( int )( e % pitch ); const int64_t k = e / pitch; y[e] = q < p ? b[perm[k] + ( int64_t )q * n] : 0.0; }
 }
-__global__ void permute_out_kernel( const double* __restrict__ y, const int* __restrict__ perm, int n, int p, double* __restrict__ x ) {
+__global__ void permute_out_kernel( const double* __restrict__ y, const int* __restrict__ perm, int n, int p, int pitch, double* __restrict__ x ) {
   int64_t e = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tot = ( int64_t )n * p, stride = ( int64_t )gridDim.x * blockDim.x;
-  for ( ; e < tot; e += stride ) { int k = ( int )( e % n ); int64_t c = e / n; x[perm[k] + c * n] = y[e]; }
+  for ( ; e < tot; e += stride ) { const int k = ( int )( e % n ); const int64_t q = e / n; x[perm[k] + q * n] = y[( int64_t )k * pitch + q]; }
 }
 
 /* forward: add the children's update vectors into the parent's pivots (y) and update rows (w).
@@ -913,11 +941,10 @@ __global__ void permute_out_kernel( const double* __restrict__ y, const int* __r
 constexpr int GATHER_ROWS = 2048;
 struct GatherTask { int parent; int lo; int hi; };
 __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const GatherTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const int* __restrict__ child_list,
-                                                            const int* __restrict__ relidx, double* __restrict__ y, int n, int p,
-                                                            double* __restrict__ w_parent, int64_t ldw_parent, const double* __restrict__ w_child, int64_t ldw_child ) {
+                                                            const int* __restrict__ relidx, double* __restrict__ y, int pitch,
+                                                            double* __restrict__ w_parent, const double* __restrict__ w_child ) {
   const GatherTask t = tasks[blockIdx.x];
   const SnMeta P = sn[t.parent];
-  const int pc0 = blockIdx.y * PC, pcn = min( PC, p - pc0 );
   for ( int ci = P.child_begin; ci < P.child_end; ci++ ) {
     const SnMeta C = sn[child_list[ci]];
     const int uc = C.f - C.k;
@@ -927,271 +954,295 @@ __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const GatherTask* __
       { int x = 0, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.lo ) x = m + 1; else z = m; } a = x; }
       { int x = a, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.hi ) x = m + 1; else z = m; } b = x; }
     }
-    for ( int i = a + threadIdx.x; i < b; i += blockDim.x ) {
+    const int64_t tot = ( int64_t )( b - a ) * pitch;
+    for ( int64_t e = threadIdx.x; e < tot; e += blockDim.x ) {
+      const int i = a + ( int )( e / pitch ), q = ( int )( e % pitch );
       const int d = rel[i];
-      for ( int q = 0; q < pcn; q++ ) {
-        const double v = w_child[C.wptr + i + ( int64_t )( pc0 + q ) * ldw_child];
-        if ( d < P.k ) y[P.c0 + d + ( int64_t )( pc0 + q ) * n] += v;
-        else w_parent[P.wptr + ( d - P.k ) + ( int64_t )( pc0 + q ) * ldw_parent] += v;
-      }
+      const double v = w_child[( C.wptr + i ) * pitch + q];
+      if ( d < P.k ) y[( int64_t )( P.c0 + d ) * pitch + q] += v;
+      else w_parent[( P.wptr + ( d - P.k ) ) * pitch + q] += v;
     }
     __syncthreads();
   }
 }
+/* backward: xg[update row i of s] = x[global row], for every supernode of a level (x of the ancestors is final) */
+__global__ void __launch_bounds__( 256 ) bwd_gather_kernel( const GatherTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const int* __restrict__ rowidx,
+                                                            const double* __restrict__ x, int pitch, double* __restrict__ xg ) {
+  const GatherTask t = tasks[blockIdx.x];
+  const SnMeta S = sn[t.parent];
+  const int* ri = rowidx + S.rowptr + S.k;
+  const int64_t tot = ( int64_t )( t.hi - t.lo ) * pitch;
+  for ( int64_t e = threadIdx.x; e < tot; e += blockDim.x ) {
+    const int i = t.lo + ( int )( e / pitch ), q = ( int )( e % pitch );
+    xg[( S.wptr + i ) * pitch + q] = x[( int64_t )ri[i] * pitch + q];
+  }
+}
 
-/* ---- sweeps over SB-column pivot blocks ------------------------------------------------------
- * A supernode's k pivot columns are cut into solve blocks of SB = 256 columns.  For every block
- * the factorization leaves behind the explicit inverse of its triangular diagonal block
- * (build_sinv_kernel), so one sweep step per block is
- *     forward :  z_b = X_b y_b ;  y[rows below] -= L[rows below, b] z_b
- *     backward:  x[cols before] -= L[rows of b, cols before]' x_b ;  x_{b-1} = X_{b-1}' (...)
- * Both are streaming passes over a slab of the panel and are spread over many CTAs.  The small
- * triangular product that produces the NEXT block's z (or x) is done by the last CTA to finish
- * among the few tiles that own that block's rows (columns) -- an atomic ticket, no spinning --
- * while the other CTAs of the launch are still streaming.  One launch per step and tree level. */
-constexpr int SB = 256;        /* solve block width (= threads per CTA)   */
-constexpr int FT_ROWS = 64;    /* rows per forward tile                   */
-constexpr int BT_COLS = 32;    /* columns per backward tile (4 per warp)  */
-constexpr int BWD_CH = 512;    /* rows staged in shared memory per pass   */
-
-struct SolveBlk {
-  int sn;
-  int j0, nb;          /* fwd: pivot block [j0,j0+nb) whose z multiplies the rows below it.
-                          bwd: front rows [j0,j0+nb) whose x feeds the columns before min(j0,k) */
-  int la_j0, la_nb;    /* look-ahead pivot block finished by its la_tiles tiles (la_nb = 0: none) */
-  int la_tiles;
-  int64_t la_inv;      /* offset of that block's solve inverse */
-  int64_t la_part;     /* offset (rows) of its la_tiles x la_nb partial products in the scratch buffer */
-};
-
-/* The triangular product that finishes the look-ahead block, out = M v (M = X forward, X' backward; nb <= SB),
- * is split by COLUMN chunks of M: the tile that has just produced chunk j of v (64 values forward, 32 backward)
- * multiplies its own columns of M into a partial vector; the last tile to arrive (atomic ticket, no spinning)
- * adds the partial vectors in chunk order -- a fixed order, so the result does not depend on timing.
- * vs: the chunk's values in shared memory, [CW][PCT].  Returns after the last tile has written out[]. */
-template <int PCT, int CW, bool FWD>
-__device__ __forceinline__ void la_finish( const double* __restrict__ Minv, int nb, int j, int nch, const double ( *vs )[PCT], double* __restrict__ part, int64_t part_row0,
-                                           double* out, int64_t ldo, int p, int pc0, int pcn, unsigned int* tk, int* is_last ) {
-  const int tid = threadIdx.x;
-  const int c0 = j * CW, cw = min( CW, nb - c0 );
-  /* rows of M that are non-zero in these columns: forward (lower) r >= c0 rounded down to its 64-block;
-   * backward (upper) r < end of the 64-block holding the chunk's last column */
-  const int r_lo = FWD ? ( c0 & ~63 ) : 0, r_hi = FWD ? nb : min( nb, ( ( c0 + cw - 1 ) | 63 ) + 1 );
-  if ( nch > 1 ) {
-    if ( tid >= r_lo && tid < r_hi ) {
-      double acc[PCT];
+/* dest (-)= M v, outputs = rows of M (M is N x K column-major): 64 output rows per CTA, thread = (row, one of 4 chunk lanes).
+ * Round j: chunk lane g forms the chain of chunk 4j+g; the chunk sums are then subtracted in chunk order by lane 0.
+ * Lanes of a warp run down the rows of a column of M: coalesced. */
+template <int PCT>
+__global__ void __launch_bounds__( 256 ) sv_gemv_kernel( const SvTask* __restrict__ tasks, const SvTile* __restrict__ tiles, SvBases B, int p, int pitch ) {
+  __shared__ double vs[4 * KC][PCT];
+  __shared__ double part[3][KC][PCT];
+  const SvTile tl = tiles[blockIdx.x];
+  const SvTask t = tasks[tl.task];
+  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
+  const int tid = threadIdx.x, r = tid & ( KC - 1 ), g = tid >> 6;
+  const int row = tl.o0 + r;
+  const bool live = row < t.N;
+  const double* v = B.b[t.vsel] + t.voff * pitch + pc0;
+  double* dest = B.b[t.dsel] + ( t.doff + row ) * pitch + pc0;
+  /* reduction window of this tile: lower triangular -> k < o0 + 64, upper -> k >= o0 (o0 is a multiple of 64: whole chunks) */
+  const int k_lo = t.tri == 2 ? tl.o0 : 0, k_hi = t.tri == 1 ? min( t.K, tl.o0 + KC ) : t.K;
+  double cr[PCT];
 #pragma unroll
-      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-      const double* Mr = Minv + tid + ( int64_t )c0 * nb;
-      for ( int c = 0; c < cw; c += 16 ) {
+  for ( int q = 0; q < PCT; q++ ) cr[q] = ( t.mode == 0 && live && g == 0 && q < pcn ) ? dest[q] : 0.0;
+  const double* Mr = t.M + row;
+  for ( int kb = k_lo; kb < k_hi; kb += 4 * KC ) {
+    __syncthreads();
+    for ( int e = tid; e < 4 * KC * PCT; e += 256 ) { const int kk = e / PCT, q = e % PCT; vs[kk][q] = ( kb + kk < k_hi && q < pcn ) ? v[( int64_t )( kb + kk ) * pitch + q] : 0.0; }
+    __syncthreads();
+    const int k0 = kb + g * KC, kn = min( KC, k_hi - k0 );      /* my chunk: [k0, k0 + kn) */
+    double acc[PCT];
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+    if ( kn > 0 && live ) {
+      const double* Mc = Mr + ( int64_t )k0 * t.ld;
+      for ( int c = 0; c < kn; c += 16 ) {
         double mv[16];
 #pragma unroll
-        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < cw ) ? __ldg( Mr + ( int64_t )( c + i ) * nb ) : 0.0;
+        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < kn ) ? Mc[( int64_t )( c + i ) * t.ld] : 0.0;      /* 16 independent coalesced loads in flight */
 #pragma unroll
         for ( int i = 0; i < 16; i++ ) {
-          const int ci = min( c + i, cw - 1 );
 #pragma unroll
-          for ( int q = 0; q < PCT; q++ ) acc[q] += mv[i] * vs[ci][q];
+          for ( int q = 0; q < PCT; q++ ) acc[q] = fma( mv[i], vs[g * KC + c + i][q], acc[q] );              /* beyond kn: mv = 0 and vs = 0 */
         }
       }
-      double* pr = part + ( part_row0 + ( int64_t )j * nb + tid ) * p + pc0;
-#pragma unroll
-      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) pr[q] = acc[q];
     }
-    __threadfence();
-    __syncthreads();
-    if ( tid == 0 ) {
-      const unsigned int old = atomicAdd( tk, 1u );
-      *is_last = ( old == ( unsigned int )( nch - 1 ) );
-      if ( *is_last ) *tk = 0u;
+    if ( g > 0 ) {
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) part[g - 1][r][q] = acc[q];
     }
     __syncthreads();
-    if ( !*is_last ) return;
-    __threadfence();
-    if ( tid < nb ) {
-      const int j_lo = FWD ? 0 : ( tid & ~63 ) / CW, j_hi = FWD ? min( nch, ( ( tid | 63 ) + CW ) / CW ) : nch;
-      double acc[PCT];
+    if ( g == 0 ) {
 #pragma unroll
-      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-      for ( int jj = j_lo; jj < j_hi; jj++ ) {
-        const double* pr = part + ( part_row0 + ( int64_t )jj * nb + tid ) * p + pc0;
-#pragma unroll
-        for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) acc[q] += __ldcg( pr + q );
+      for ( int q = 0; q < PCT; q++ ) {
+        double c_ = cr[q] - acc[q];
+        if ( kb + KC < k_hi ) c_ -= part[0][r][q];
+        if ( kb + 2 * KC < k_hi ) c_ -= part[1][r][q];
+        if ( kb + 3 * KC < k_hi ) c_ -= part[2][r][q];
+        cr[q] = c_;
       }
-#pragma unroll
-      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) out[tid + ( int64_t )q * ldo] = acc[q];
     }
-  } else {
-    /* a single chunk: this tile finishes the block on its own */
-    if ( tid < nb ) {
-      double acc[PCT];
+  }
+  if ( g == 0 && live ) {
 #pragma unroll
-      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-      const double* Mr = Minv + tid;
-      for ( int c = 0; c < cw; c += 16 ) {
-        double mv[16];
-#pragma unroll
-        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < cw ) ? __ldg( Mr + ( int64_t )( c + i ) * nb ) : 0.0;
-#pragma unroll
-        for ( int i = 0; i < 16; i++ ) {
-          const int ci = min( c + i, cw - 1 );
-#pragma unroll
-          for ( int q = 0; q < PCT; q++ ) acc[q] += mv[i] * vs[ci][q];
-        }
-      }
-#pragma unroll
-      for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) out[tid + ( int64_t )q * ldo] = acc[q];
-    }
+    for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) dest[q] = t.mode == 0 ? cr[q] : -cr[q];
   }
 }
 
-/* z_0 = X_0 y_0 for the first block of every supernode of a level: one CTA per 64-column chunk of X_0 */
+/* dest -= M' v, outputs = columns of M (M is K x N column-major, the reduction runs down the contiguous rows): 32 output columns per
+ * CTA, 4 per warp.  Per chunk of 64 rows a warp brings its 64 x 4 slab in with coalesced loads (the next chunk is already in
+ * flight), parks it in shared memory, and lanes 0..3 run the canonical chains -- the FMA work is 1/8 of a percent of the pipe,
+ * the kernel streams. */
+constexpr int GT_COLS = 32;
+constexpr int GT_XS = 512;      /* rows of v staged per pass */
 template <int PCT>
-__global__ void __launch_bounds__( SB ) solve_first_block_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                                 const double* __restrict__ sinvF, const double* y, double* Z, int n, int p,
-                                                                 double* __restrict__ part, unsigned int* __restrict__ tickets ) {
-  __shared__ double ys[FT_ROWS][PCT];
-  __shared__ int is_last;
-  const RowTile rt = tiles[blockIdx.x];
-  const SolveBlk b = blks[rt.task];
-  const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
-  const int j = rt.r0 / FT_ROWS, cw = min( FT_ROWS, b.la_nb - rt.r0 );
-  for ( int e = threadIdx.x; e < cw * PCT; e += SB ) { const int c = e % cw, q = e / cw; ys[c][q] = q < pcn ? y[S.c0 + b.la_j0 + rt.r0 + c + ( int64_t )( pc0 + q ) * n] : 0.0; }
-  __syncthreads();
-  la_finish<PCT, FT_ROWS, true>( sinvF + b.la_inv, b.la_nb, j, b.la_tiles, ys, part, b.la_part, Z + S.c0 + b.la_j0 + ( int64_t )pc0 * n, n, p, pc0, pcn,
-                                 tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
-}
-
-/* forward step: 64 rows x nb columns per CTA, thread = (row, column quarter) */
-template <int PCT>
-__global__ void __launch_bounds__( SB ) solve_fwd_step_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                              const double* __restrict__ L, const double* __restrict__ sinvF,
-                                                              double* y, double* Z, int n, int p, double* w, int64_t ldw, double* __restrict__ part, unsigned int* __restrict__ tickets ) {
-  __shared__ double zs[SB][PCT];
-  __shared__ double red[3][PCT][FT_ROWS];
-  __shared__ double ys[FT_ROWS][PCT];
-  __shared__ int is_last;
-  const RowTile rt = tiles[blockIdx.x];
-  const SolveBlk b = blks[rt.task];
-  const SnMeta S = sn[b.sn];
-  const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
-  const int nb = b.nb, tid = threadIdx.x;
-  for ( int e = tid; e < nb * PCT; e += SB ) { const int c = e % nb, q = e / nb; zs[c][q] = q < pcn ? Z[S.c0 + b.j0 + c + ( int64_t )( pc0 + q ) * n] : 0.0; }
-  __syncthreads();
-  const int r = tid & ( FT_ROWS - 1 ), cq = tid >> 6;
-  const int lr = b.j0 + nb + rt.r0 + r;       /* front-local row */
-  double acc[PCT];
-#pragma unroll
-  for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-  if ( lr < S.f ) {
-    const double* Lr = L + S.lptr + lr + ( int64_t )b.j0 * S.ld;
-    for ( int c = cq; c < nb; c += 64 ) {
-      double lv[16];
-#pragma unroll
-      for ( int i = 0; i < 16; i++ ) lv[i] = ( c + 4 * i < nb ) ? Lr[( int64_t )( c + 4 * i ) * S.ld] : 0.0;      /* 16 independent coalesced loads */
-#pragma unroll
-      for ( int i = 0; i < 16; i++ ) {
-        const int ci = min( c + 4 * i, nb - 1 );     /* never touch uninitialised shared memory: 0 * NaN = NaN */
-#pragma unroll
-        for ( int q = 0; q < PCT; q++ ) acc[q] += lv[i] * zs[ci][q];
-      }
-    }
-  }
-  if ( cq > 0 ) {
-#pragma unroll
-    for ( int q = 0; q < PCT; q++ ) red[cq - 1][q][r] = acc[q];
-  }
-  __syncthreads();
-  const bool la = b.la_nb > 0 && rt.r0 < b.la_tiles * FT_ROWS;      /* this tile owns rows of the next pivot block */
-  if ( cq == 0 ) {
-#pragma unroll
-    for ( int q = 0; q < PCT; q++ ) {
-      double yn = 0.0;
-      if ( q < pcn && lr < S.f ) {
-        const double v = ( ( acc[q] + red[0][q][r] ) + red[1][q][r] ) + red[2][q][r];
-        if ( lr < S.k ) { double* yp = y + S.c0 + lr + ( int64_t )( pc0 + q ) * n; yn = *yp - v; *yp = yn; }
-        else w[S.wptr + ( lr - S.k ) + ( int64_t )( pc0 + q ) * ldw] -= v;
-      }
-      if ( la ) ys[r][q] = yn;
-    }
-  }
-  if ( !la ) return;
-  __syncthreads();
-  la_finish<PCT, FT_ROWS, true>( sinvF + b.la_inv, b.la_nb, rt.r0 / FT_ROWS, b.la_tiles, ys, part, b.la_part, Z + S.c0 + b.la_j0 + ( int64_t )pc0 * n, n, p, pc0, pcn,
-                                 tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
-}
-
-/* backward step: x[c] -= sum_r M[r, c] x[r] for 32 columns per CTA (4 per warp; lanes run down the rows,
- * coalesced) over the rows [j0, j0+nb) of the front: either a pivot block whose x has just been finished,
- * or the update rows below the pivots (x gathered through the row list).  M = L panel (L' x) or U' panel (U x). */
-template <int PCT>
-__global__ void __launch_bounds__( SB ) solve_bwd_step_kernel( const SolveBlk* __restrict__ blks, const RowTile* __restrict__ tiles, const SnMeta* __restrict__ sn,
-                                                              const double* __restrict__ M, const double* __restrict__ sinvB, const int* __restrict__ rowidx,
-                                                              double* x, int n, int p, double* __restrict__ part, unsigned int* __restrict__ tickets ) {
-  __shared__ double xs[PCT][BWD_CH];      /* [rhs][row]: lanes read consecutive rows, no bank conflicts */
-  __shared__ double vn[BT_COLS][PCT];
-  __shared__ int is_last;
-  const RowTile rt = tiles[blockIdx.x];
-  const SolveBlk b = blks[rt.task];
-  const SnMeta S = sn[b.sn];
+__global__ void __launch_bounds__( 256 ) sv_gemvT_kernel( const SvTask* __restrict__ tasks, const SvTile* __restrict__ tiles, SvBases B, int p, int pitch ) {
+  __shared__ double xs[GT_XS][PCT];
+  __shared__ double slab[8][4][KC + 1];
+  const SvTile tl = tiles[blockIdx.x];
+  const SvTask t = tasks[tl.task];
   const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool gather = b.j0 >= S.k;
-  const int climit = min( b.j0, S.k );
-  const int cbase = rt.r0 + warp * 4;
-  const int* ri = rowidx + S.rowptr;
-  double acc[4][PCT];
+  const int cbase = tl.o0 + warp * 4;
+  const double* v = B.b[t.vsel] + t.voff * pitch + pc0;
+  const int mycol = cbase + ( lane & 3 );
+  double* dest = B.b[t.dsel] + ( t.doff + mycol ) * pitch + pc0;
+  const bool owner = lane < 4 && mycol < t.N;
+  double cr[PCT];
 #pragma unroll
-  for ( int j = 0; j < 4; j++ )
-#pragma unroll
-    for ( int q = 0; q < PCT; q++ ) acc[j][q] = 0.0;
-  for ( int rc = 0; rc < b.nb; rc += BWD_CH ) {
-    const int rows = min( BWD_CH, b.nb - rc );
-    __syncthreads();
-    for ( int e = tid; e < rows * PCT; e += SB ) {
-      const int r = e % rows, q = e / rows;
-      const int lr = b.j0 + rc + r;
-      const int g = gather ? ri[lr] : S.c0 + lr;
-      xs[q][r] = q < pcn ? x[g + ( int64_t )( pc0 + q ) * n] : 0.0;
-    }
-    __syncthreads();
+  for ( int q = 0; q < PCT; q++ ) cr[q] = ( owner && q < pcn ) ? dest[q] : 0.0;
+  const int ncol = max( 0, min( 4, t.N - cbase ) );
+  const double* Mw = t.M + ( int64_t )cbase * t.ld;
+  double pre[8];
+  auto fetch = [&]( int k0 ) {
 #pragma unroll
     for ( int j = 0; j < 4; j++ ) {
-      if ( cbase + j >= climit ) continue;
-      const double* col = M + S.lptr + ( b.j0 + rc ) + ( int64_t )( cbase + j ) * S.ld;
-      for ( int r = lane; r < rows; r += 256 ) {
-        double lv[8];
 #pragma unroll
-        for ( int i = 0; i < 8; i++ ) lv[i] = ( r + 32 * i < rows ) ? col[r + 32 * i] : 0.0;
+      for ( int h = 0; h < 2; h++ ) { const int k = k0 + lane + 32 * h; pre[2 * j + h] = ( j < ncol && k < t.K ) ? Mw[k + ( int64_t )j * t.ld] : 0.0; }
+    }
+  };
+  if ( t.K > 0 ) fetch( 0 );
+  for ( int kb = 0; kb < t.K; kb += GT_XS ) {
+    const int rows = min( GT_XS, t.K - kb );
+    __syncthreads();
+    for ( int e = tid; e < rows * PCT; e += 256 ) { const int kk = e / PCT, q = e % PCT; xs[kk][q] = q < pcn ? v[( int64_t )( kb + kk ) * pitch + q] : 0.0; }
+    __syncthreads();
+    for ( int k0 = 0; k0 < rows; k0 += KC ) {
 #pragma unroll
-        for ( int i = 0; i < 8; i++ ) {
-          const int ri2 = min( r + 32 * i, rows - 1 );
+      for ( int j = 0; j < 4; j++ ) { slab[warp][j][lane] = pre[2 * j]; slab[warp][j][lane + 32] = pre[2 * j + 1]; }
+      if ( kb + k0 + KC < t.K ) fetch( kb + k0 + KC );
+      __syncwarp();
+      if ( owner ) {
+        const int kn = min( KC, rows - k0 );
+        double acc[PCT];
 #pragma unroll
-          for ( int q = 0; q < PCT; q++ ) acc[j][q] += lv[i] * xs[q][ri2];
+        for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+        const double* sl = slab[warp][lane & 3];
+        for ( int i = 0; i < kn; i++ ) {
+          const double m = sl[i];
+#pragma unroll
+          for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, xs[k0 + i][q], acc[q] );
+        }
+#pragma unroll
+        for ( int q = 0; q < PCT; q++ ) cr[q] -= acc[q];
+      }
+      __syncwarp();
+    }
+  }
+  if ( owner ) {
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) dest[q] = cr[q];
+  }
+}
+
+/* ---- the same task lists on the FP64 tensor pipe (p >= 5): C'[p x N] (-)= V'[p x K] * Mop[N x K]'  with the right-hand sides as
+ * the M dimension of the tile.  V' (lda = pitch) and a gemv-type M (ldb = ld) are "NT" operands exactly as in the factorization
+ * kernel; a gemvT-type M has the reduction index contiguous, so its tile is staged n-major by one bulk copy of 16 rows per column
+ * (BT = true).  Every KC k-steps the accumulators are flushed into the running C registers: the canonical arithmetic above.
+ * grid.y walks over the 64-wide slices of the right-hand sides. */
+struct SvGemm { double* C; const double* A; const double* B; int ldc, lda, ldb; int M, N, K; int mode; };
+__global__ void sv_expand_kernel( const SvTask* __restrict__ tasks, int64_t ntasks, SvBases Bs, int p, int pitch, SvGemm* __restrict__ out ) {
+  const int64_t i = ( int64_t )blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= ntasks ) return;
+  const SvTask t = tasks[i];
+  SvGemm g;
+  g.C = Bs.b[t.dsel] + t.doff * pitch; g.A = Bs.b[t.vsel] + t.voff * pitch; g.B = t.M;
+  g.ldc = pitch; g.lda = pitch; g.ldb = t.ld; g.M = p; g.N = t.N; g.K = t.K; g.mode = t.mode;
+  out[i] = g;
+}
+
+template <bool BT>
+__global__ void __launch_bounds__( 288 ) gemm_solve_dmma_kernel( const SvGemm* __restrict__ tasks, const SvTile* __restrict__ tiles, const double* __restrict__ zeros ) {
+  constexpr int BM = 64, BN = 64, WM = 32, WN = 16, STAGES = 4, BK = 16;
+  constexpr int NCW = 8, LDA = BM + 4, LDB = BT ? BK + 4 : BN + 4;
+  constexpr int BSTAGE = BT ? BN * LDB : BK * LDB;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  extern __shared__ double sm[];
+  double* As = sm;
+  double* Bs = sm + STAGES * BK * LDA;
+  uint64_t* full = reinterpret_cast<uint64_t*>( Bs + STAGES * BSTAGE );
+  uint64_t* empty = full + STAGES;
+  const SvTile tl = tiles[blockIdx.x];
+  const SvGemm t = tasks[tl.task];
+  const int m0 = blockIdx.y * BM, n0 = tl.o0;
+  if ( m0 >= t.M ) return;
+  const int mrem = t.M - m0, nrem = t.N - n0;
+  const double* Ag = t.A + m0;
+  const double* Bg = BT ? t.B + ( int64_t )n0 * t.ldb : t.B + n0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  /* 16-byte alignment of the bulk copies: NT operands are fetched one element early along m / n when they start at an odd
+   * address (sa, sb); a BT operand that starts at an odd ROW is fetched one row early and one row longer (18 rows per column
+   * and stage), and every fragment read is shifted by one (sbk) */
+  const int sa = ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ), sb = BT ? 0 : ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 ), sbk = BT ? ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 ) : 0;
+  const int K = t.K, nk = ( K + BK - 1 ) / BK;
+  if ( tid == 0 ) {
+    for ( int s = 0; s < STAGES; s++ ) { mbar_init( &full[s], 1 ); mbar_init( &empty[s], NCW ); }
+    asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
+    asm volatile( "fence.proxy.async.shared::cta;\n" ::: "memory" );
+  }
+  __syncthreads();
+  if ( warp == NCW ) {
+    /* ---------------- producer warp */
+    const int ra = ( ( min( BM, mrem ) + sa + 1 ) & ~1 ) * 8;
+    if ( !BT ) {
+      const int rb = ( ( min( BN, nrem ) + sb + 1 ) & ~1 ) * 8;
+      const int q = lane & 15; const bool isb = lane >= 16;
+      const double* g = isb ? Bg - sb : Ag - sa;
+      const int64_t ldg = isb ? t.ldb : t.lda;
+      const int bytes = isb ? rb : ra;
+      for ( int kt = 0; kt < nk; kt++ ) {
+        const int slot = kt % STAGES, use = kt / STAGES;
+        if ( lane == 0 ) { if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 ); mbar_expect_tx( &full[slot], BK * ( ra + rb ) ); }
+        __syncwarp();
+        double* dst = isb ? Bs + slot * BSTAGE + q * LDB : As + slot * BK * LDA + q * LDA;
+        const int kq = kt * BK + q;
+        bulk_g2s( dst, kq < K ? ( const void* )( g + ( int64_t )kq * ldg ) : ( const void* )zeros, bytes, &full[slot] );
+      }
+    } else {
+      /* A: lanes 0..15 one k-column each; B: every lane two columns of M, 16 contiguous rows (128 bytes) each */
+      const int nval = min( BN, nrem ), cb = ( BK + 2 * sbk ) * 8;
+      for ( int kt = 0; kt < nk; kt++ ) {
+        const int slot = kt % STAGES, use = kt / STAGES;
+        if ( lane == 0 ) { if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 ); mbar_expect_tx( &full[slot], BK * ra + nval * cb ); }
+        __syncwarp();
+        if ( lane < 16 ) { const int kq = kt * BK + lane; bulk_g2s( As + slot * BK * LDA + lane * LDA, kq < K ? ( const void* )( Ag - sa + ( int64_t )kq * t.lda ) : ( const void* )zeros, ra, &full[slot] ); }
+#pragma unroll
+        for ( int h = 0; h < 2; h++ ) { const int nn = lane + 32 * h; if ( nn < nval ) bulk_g2s( Bs + slot * BSTAGE + nn * LDB, Bg + ( int64_t )nn * t.ldb + kt * BK - sbk, cb, &full[slot] ); }
+      }
+    }
+    return;
+  }
+  /* ---------------- consumers */
+  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[MT][NTL][2], cr[MT][NTL][2];
+#pragma unroll
+  for ( int i = 0; i < MT; i++ )
+#pragma unroll
+    for ( int j = 0; j < NTL; j++ )
+#pragma unroll
+      for ( int h = 0; h < 2; h++ ) {
+        acc[i][j][h] = 0.0;
+        const int c = n0 + wn0 + j * 8 + 2 * fk + h, r = m0 + wm0 + i * 8 + fr;
+        cr[i][j][h] = ( t.mode == 0 && c < t.N && r < t.M ) ? t.C[( int64_t )c * t.ldc + r] : 0.0;
+      }
+  for ( int kt = 0; kt < nk; kt++ ) {
+    const int slot = kt % STAGES;
+    mbar_wait( &full[slot], ( kt / STAGES ) & 1 );
+    const double* as = As + slot * BK * LDA + wm0 + fr + sa;
+    const double* bs = BT ? Bs + slot * BSTAGE + ( wn0 + fr ) * LDB + sbk : Bs + slot * BSTAGE + wn0 + fr + sb;
+    const int kvalid = K - kt * BK;         /* BT: rows beyond K hold whatever follows the slab in memory -- never let them meet a product */
+#pragma unroll
+    for ( int kk = 0; kk < BK; kk += 4 ) {
+      double af[MT], bf[NTL];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
+#pragma unroll
+      for ( int j = 0; j < NTL; j++ ) bf[j] = BT ? ( kk + fk < kvalid ? bs[j * 8 * LDB + kk + fk] : 0.0 ) : bs[( kk + fk ) * LDB + j * 8];
+#pragma unroll
+      for ( int i = 0; i < MT; i++ )
+#pragma unroll
+        for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
+    }
+    __syncwarp();
+    if ( lane == 0 ) mbar_arrive( &empty[slot] );
+    if ( ( ( kt + 1 ) & ( KC / BK - 1 ) ) == 0 || kt == nk - 1 ) {      /* end of a canonical chunk */
+#pragma unroll
+      for ( int i = 0; i < MT; i++ )
+#pragma unroll
+        for ( int j = 0; j < NTL; j++ )
+#pragma unroll
+          for ( int h = 0; h < 2; h++ ) { cr[i][j][h] -= acc[i][j][h]; acc[i][j][h] = 0.0; }
+    }
+  }
+#pragma unroll
+  for ( int j = 0; j < NTL; j++ ) {
+#pragma unroll
+    for ( int h = 0; h < 2; h++ ) {
+      const int c = n0 + wn0 + j * 8 + 2 * fk + h;
+      if ( c < t.N ) {
+        double* cc = t.C + ( int64_t )c * t.ldc;
+#pragma unroll
+        for ( int i = 0; i < MT; i++ ) {
+          const int r = m0 + wm0 + i * 8 + fr;
+          if ( r < t.M ) cc[r] = t.mode == 0 ? cr[i][j][h] : -cr[i][j][h];
         }
       }
     }
   }
-  const bool la = b.la_nb > 0 && rt.r0 >= b.la_j0;        /* this tile owns columns of the pivot block that ends at climit */
-#pragma unroll
-  for ( int j = 0; j < 4; j++ ) {
-#pragma unroll
-    for ( int q = 0; q < PCT; q++ ) {
-      double v = acc[j][q];
-      for ( int o = 16; o; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
-      if ( lane == 0 ) {
-        double xn = 0.0;
-        if ( q < pcn && cbase + j < climit ) { double* xp = x + S.c0 + cbase + j + ( int64_t )( pc0 + q ) * n; xn = *xp - v; *xp = xn; }
-        if ( la ) vn[warp * 4 + j][q] = xn;
-      }
-    }
-  }
-  if ( !la ) return;
-  __syncthreads();
-  double* xb = x + S.c0 + b.la_j0 + ( int64_t )pc0 * n;
-  la_finish<PCT, BT_COLS, false>( sinvB + b.la_inv, b.la_nb, ( rt.r0 - b.la_j0 ) / BT_COLS, b.la_tiles, vn, part, b.la_part, xb, n, p, pc0, pcn,
-                                  tickets + ( int64_t )rt.task * gridDim.y + blockIdx.y, &is_last );
 }
 
 /* ---- explicit inverses of the SB-wide triangular diagonal blocks, from the panel and the 64x64 inverses the
@@ -1203,7 +1254,8 @@ struct SinvTask {
   int j0, nb, jb;               /* solve block [j0, j0+nb), block column jb of it       */
   const double* inv64;          /* 64x64 inverses of the supernode (block i at +i*4096) */
   const int* piv;               /* LU: pivots of the supernode's columns (NULL: none)   */
-  double* X; double* XT;        /* nb x nb outputs, ld nb (XT may be NULL)              */
+  double* X; double* XT;        /* nb x nb outputs, leading dimension ldx (XT may be NULL) */
+  int ldx;                      /* nb rounded up to even: 16-byte aligned columns for the bulk copies of the tensor-path sweeps */
 };
 constexpr int SINV_SMEM = 3 * NB * ( NB + 1 ) * 8 + NB * 4;
 
@@ -1248,7 +1300,7 @@ __global__ void __launch_bounds__( 256 ) build_sinv_kernel( const SinvTask* __re
         for ( int e = tid; e < NB * NB; e += 256 ) {
           const int r = e % NB, c = e / NB;
           As[r][c] = ( r < hi && c < wq ) ? t.P[( t.j0 + NB * i + r ) + ( int64_t )( t.j0 + NB * q + c ) * t.ld] : 0.0;
-          Bs[r][c] = ( r < wq && c < wj ) ? t.X[( NB * q + r ) + ( int64_t )( NB * jb + c ) * nb] : 0.0;
+          Bs[r][c] = ( r < wq && c < wj ) ? t.X[( NB * q + r ) + ( int64_t )( NB * jb + c ) * t.ldx] : 0.0;
         }
         __syncthreads();
         for ( int kk = 0; kk < NB; kk++ ) {
@@ -1288,13 +1340,13 @@ __global__ void __launch_bounds__( 256 ) build_sinv_kernel( const SinvTask* __re
         const int r = tr + a, cc = tc + c;
         if ( r < hi && cc < wj ) {
           const int gr = NB * i + r, gc = NB * jb + cc;
-          t.X[gr + ( int64_t )gc * nb] = acc[a][c];
-          if ( t.XT ) t.XT[gc + ( int64_t )gr * nb] = acc[a][c];
+          t.X[gr + ( int64_t )gc * t.ldx] = acc[a][c];
+          if ( t.XT ) t.XT[gc + ( int64_t )gr * t.ldx] = acc[a][c];
         }
       }
     /* blocks above the diagonal of this block column are zero */
     if ( i == jb ) {
-      for ( int e = tid; e < NB * jb * wj; e += 256 ) { const int r = e % ( NB * jb ), c = e / ( NB * jb ); t.X[r + ( int64_t )( NB * jb + c ) * nb] = 0.0; if ( t.XT ) t.XT[( NB * jb + c ) + ( int64_t )r * nb] = 0.0; }
+      for ( int e = tid; e < NB * jb * wj; e += 256 ) { const int r = e % ( NB * jb ), c = e / ( NB * jb ); t.X[r + ( int64_t )( NB * jb + c ) * t.ldx] = 0.0; if ( t.XT ) t.XT[( NB * jb + c ) + ( int64_t )r * t.ldx] = 0.0; }
     }
   }
 }

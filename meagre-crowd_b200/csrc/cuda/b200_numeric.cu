@@ -81,6 +81,8 @@ constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_THREADS = 256;
 constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
+constexpr int SVG_SMEM_NT = GEMM_STAGES * 16 * ( 68 + 68 ) * 8 + 2 * GEMM_STAGES * 8;                 /* gemm_solve_dmma_kernel<false> */
+constexpr int SVG_SMEM_BT = GEMM_STAGES * ( 16 * 68 + 64 * 20 ) * 8 + 2 * GEMM_STAGES * 8;            /* gemm_solve_dmma_kernel<true>  */
 
 enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_DIAG_S, LK_SMALL_FRONT, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
 static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "diag_block_small", "small_front", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
@@ -93,8 +95,10 @@ struct Launch { int kind; int64_t first; int64_t count; int depth; double flops;
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
-enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_FIRST, SK_FWD_STEP, SK_BWD_STEP, SK_COUNT };
-struct SLaunch { int kind; int64_t first; int64_t count; int64_t first_tile; int64_t ntiles; int depth; };
+enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_TRI, SK_FWD_UPD, SK_BWD_GATHER, SK_BWD_UPD, SK_BWD_TRI, SK_COUNT };
+/* one launch of a sweep: gather / zero launches use first,count; product launches carry their tiles in the FMA list (t0,nt: 64 outputs per
+ * tile for gemv-type tasks, 32 for gemvT-type) and in the tensor-path list (g0,ng: 64 outputs per tile) */
+struct SLaunch { int kind; int depth; int64_t first, count; int64_t t0, nt; int64_t g0, ng; };
 
 static thread_local bool g_dry = false;   /* schedule-only mode: no CUDA call at all (b200_ctx_create_dry) */
 struct DryGuard { bool old; explicit DryGuard( bool v ) : old( g_dry ) { g_dry = v; } ~DryGuard() { g_dry = old; } };
@@ -138,11 +142,12 @@ struct b200_ctx {
   DevVec<AsmTask> asm_tasks;
   std::vector<Launch> launches;
   /* solve */
-  DevVec<SolveBlk> sblk; DevVec<RowTile> fwd_tiles, bwd_tiles; DevVec<int> gather_parents;
+  DevVec<SvTask> sv_tasks; DevVec<SvTile> sv_tiles_v, sv_tiles_t, sv_tiles_g; DevVec<GatherTask> bgather_tasks;
+  SvGemm* dSvGemm = nullptr; int sv_gemm_p = 0; int solve_wide_min = SB_WIDE_MIN;
   std::vector<SLaunch> slaunches;
-  int64_t max_blocks_per_launch = 0, sinvsize = 0, max_part_rows = 0;
-  double* dPart = nullptr; DevVec<GatherTask> gather_tasks;
-  unsigned int* dTickets = nullptr; double* dZ = nullptr;
+  int64_t sinvsize = 0;
+  DevVec<GatherTask> gather_tasks;
+  double* dZ = nullptr;
   double *dSinvF = nullptr, *dSinvB = nullptr, *dSinvTmp = nullptr;   /* solve-block inverses: X (forward), X' (backward) */
   DevVec<SinvTask> sinv_tasks;
   double *dY = nullptr, *dW[2] = { nullptr, nullptr }, *dB = nullptr, *dX = nullptr;
@@ -187,6 +192,9 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
+  CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_NT ) );
+  CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_BT ) );
+  { const char* e = getenv( "B200_SOLVE_WIDE_MIN" ); if ( e ) c->solve_wide_min = std::max( 2 * SB, atoi( e ) ); }     /* test hook: wide solve blocks on small problems */
   memset( &c->stats, 0, sizeof( c->stats ) );
   return c;
 }
@@ -230,6 +238,7 @@ extern "C" b200_ctx_t* b200_ctx_create_dry( int rank, int world ) {
   memset( &c->stats, 0, sizeof( c->stats ) );
   memset( &c->prop, 0, sizeof( c->prop ) ); c->prop.multiProcessorCount = 148;
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
+  { const char* e = getenv( "B200_SOLVE_WIDE_MIN" ); if ( e ) c->solve_wide_min = std::max( 2 * SB, atoi( e ) ); }
   return c;
 }
 
@@ -245,9 +254,9 @@ static void release_symbolic( b200_ctx* c ) {
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
   c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
   c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
-  c->small_sns.release(); c->sblk.release(); c->fwd_tiles.release(); c->bwd_tiles.release(); c->gather_parents.release(); c->gather_tasks.release();
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart );
-  c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->dPart = nullptr;
+  c->small_sns.release(); c->sv_tasks.release(); c->sv_tiles_v.release(); c->sv_tiles_t.release(); c->sv_tiles_g.release(); c->gather_tasks.release(); c->bgather_tasks.release();
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dSvGemm );
+  c->dR = c->dD = c->dZ = nullptr; c->dSvGemm = nullptr; c->sv_gemm_p = 0;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
   c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
   c->factored = false; c->device_bytes = 0;
@@ -320,7 +329,9 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     m.c0 = S->sn_start[s]; m.k = S->sn_start[s + 1] - S->sn_start[s]; m.f = ( int )( S->rowptr[s + 1] - S->rowptr[s] );
     m.parent = S->sn_parent[s]; m.depth = S->sn_depth[s]; m.child_begin = child_cnt[s]; m.child_end = child_cnt[s + 1]; m.ld = ( m.f + 1 ) & ~1;
     m.invptr = invoff; invoff += ( int64_t )( m.k / NB ) * NB * NB + ( int64_t )( m.k % NB ) * ( m.k % NB );
-    m.sinv = sinvoff; sinvoff += ( int64_t )( m.k / SB ) * SB * SB + ( int64_t )( m.k % SB ) * ( m.k % SB );
+    m.sbw = m.k >= c->solve_wide_min ? SB_WIDE : SB;
+    { const int64_t full = m.k / m.sbw, rem = m.k % m.sbw;      /* block t of the supernode at m.sinv + t * sbw^2, leading dimension = its width rounded up to even */
+      m.sinv = sinvoff; sinvoff += full * m.sbw * m.sbw + ( ( rem + 1 ) & ~( int64_t )1 ) * rem; }
     const int d = m.depth; const int64_t u = m.f - m.k;
     levels[d].push_back( s );
     c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u + 1 ) & ~( int64_t )1 ) * u );
@@ -348,14 +359,16 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   if ( !c->dry ) {
   size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
   if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
-  CK( cudaMalloc( &c->dL, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
-  if ( LU ) CK( cudaMalloc( &c->dU, std::max<int64_t>( c->lsize, 1 ) * 8 ) );
+  CK( cudaMalloc( &c->dL, ( std::max<int64_t>( c->lsize, 1 ) + 32 ) * 8 ) );     /* + slack: the row-run copies of the backward tensor-path sweep read up to 17 rows past a slab */
+  CK( cudaMemset( c->dL + std::max<int64_t>( c->lsize, 1 ), 0, 32 * 8 ) );
+  if ( LU ) { CK( cudaMalloc( &c->dU, ( std::max<int64_t>( c->lsize, 1 ) + 32 ) * 8 ) ); CK( cudaMemset( c->dU + std::max<int64_t>( c->lsize, 1 ), 0, 32 * 8 ) ); }
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dCB[a], std::max<int64_t>( c->cb_arena[a], 2 ) * 8 ) );
   CK( cudaMalloc( &c->dInv, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) );     /* + slack: the bulk copies of an odd-aligned block read one double past it */
   if ( LU ) { CK( cudaMalloc( &c->dInv2, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
-  CK( cudaMalloc( &c->dSinvF, std::max<int64_t>( sinvoff, 1 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
-  if ( LU ) CK( cudaMalloc( &c->dSinvTmp, std::max<int64_t>( sinvoff, 1 ) * 8 ) );
+  CK( cudaMalloc( &c->dSinvF, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );
+  CK( cudaMemset( c->dSinvF, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvB, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );     /* padding rows of odd blocks stay zero */
+  if ( LU ) { CK( cudaMalloc( &c->dSinvTmp, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvTmp, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); }
   }
   c->device_bytes = ( int64_t )need;
   { std::vector<int64_t> v( S->amap, S->amap + S->nnzA ); if ( c->amap.upload( v ) ) return B200_ERR_CUDA; }
@@ -696,11 +709,11 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     std::vector<SinvTask> sv;
     for ( int s = 0; s < ns; s++ ) {
       const SnMeta& m = meta[s];
-      for ( int j0 = 0; j0 < m.k; j0 += SB ) {
-        const int nb = std::min( SB, m.k - j0 );
-        const int64_t off = m.sinv + ( int64_t )( j0 / SB ) * SB * SB;
+      for ( int j0 = 0; j0 < m.k; j0 += m.sbw ) {
+        const int nb = std::min( m.sbw, m.k - j0 );
+        const int64_t off = m.sinv + ( int64_t )( j0 / m.sbw ) * m.sbw * m.sbw;
         for ( int jb = 0; jb * NB < nb; jb++ ) {
-          SinvTask x; x.P = Lb + m.lptr; x.ld = m.ld; x.j0 = j0; x.nb = nb; x.jb = jb; x.inv64 = c->dInv + m.invptr;
+          SinvTask x; x.P = Lb + m.lptr; x.ld = m.ld; x.j0 = j0; x.nb = nb; x.jb = jb; x.inv64 = c->dInv + m.invptr; x.ldx = ( nb + 1 ) & ~1;
           x.piv = LU ? c->dPiv + m.c0 : nullptr; x.X = c->dSinvF + off; x.XT = LU ? nullptr : c->dSinvB + off;
           sv.push_back( x );
           if ( LU ) { SinvTask y = x; y.P = Ub + m.lptr; y.inv64 = c->dInv2 + m.invptr; y.piv = nullptr; y.X = c->dSinvTmp + off; y.XT = c->dSinvB + off; sv.push_back( y ); }
@@ -709,79 +722,82 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
     if ( c->sinv_tasks.upload( sv ) ) return B200_ERR_CUDA;
   }
-  /* ---- solve schedule: forward deepest->root, backward root->deepest; one launch per SB-column step of a level */
-  std::vector<SolveBlk> sb; std::vector<RowTile> ft, bt; std::vector<GatherTask> gp;
-  std::vector<SLaunch>& SS = c->slaunches;
-  c->max_blocks_per_launch = 0; c->max_part_rows = 0;
-  for ( int d = S->maxdepth; d >= 0; d-- ) {
-    const std::vector<int>& lv = levels[d];
-    if ( c->level_w[d] > 0 ) SS.push_back( { SK_FWD_ZERO_W, d & 1, c->level_w[d], 0, 0, d } );
-    { const int64_t g0 = ( int64_t )gp.size();
-      for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
-        if ( any ) for ( int lo = 0; lo < meta[s].f; lo += GATHER_ROWS ) gp.push_back( { s, lo, std::min( meta[s].f, lo + GATHER_ROWS ) } ); }
-      if ( ( int64_t )gp.size() > g0 ) SS.push_back( { SK_FWD_GATHER, g0, ( int64_t )gp.size() - g0, 0, 0, d } ); }
-    { const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size(); int64_t prow = 0;
-      for ( int s : lv ) { const SnMeta& m = meta[s]; SolveBlk x; x.sn = s; x.j0 = 0; x.nb = 0; x.la_j0 = 0; x.la_nb = std::min( SB, m.k ); x.la_tiles = ( x.la_nb + FT_ROWS - 1 ) / FT_ROWS; x.la_inv = m.sinv;
-        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
-        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
-        for ( int j = 0; j < x.la_tiles; j++ ) ft.push_back( { id, j * FT_ROWS } ); }
-      c->max_part_rows = std::max( c->max_part_rows, prow );
-      c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
-      SS.push_back( { SK_FWD_FIRST, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } ); }
-    int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
-    for ( int j0 = 0; j0 < maxk; j0 += SB ) {
-      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )ft.size(); int64_t prow = 0;
-      for ( int s : lv ) {
-        const SnMeta& m = meta[s]; if ( j0 >= m.k ) continue;
-        const int nb = std::min( SB, m.k - j0 ); const int below = m.f - j0 - nb;
-        if ( below <= 0 ) continue;
-        const int nbn = std::min( SB, m.k - ( j0 + nb ) );
-        SolveBlk x; x.sn = s; x.j0 = j0; x.nb = nb; x.la_j0 = j0 + nb; x.la_nb = std::max( nbn, 0 ); x.la_tiles = ( x.la_nb + FT_ROWS - 1 ) / FT_ROWS; x.la_inv = m.sinv + ( int64_t )( j0 / SB + 1 ) * SB * SB;
-        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
-        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
-        for ( int r0 = 0; r0 < below; r0 += FT_ROWS ) ft.push_back( { id, r0 } );
+  /* ---- solve schedule: forward deepest->root, backward root->deepest.  Per level and block step two launches: the triangular product
+   * with the block's explicit inverse, then the update of everything the block feeds (kernels: sv_gemv / sv_gemvT, or the tensor path) */
+  {
+    std::vector<SvTask> tk; std::vector<SvTile> tv, tt, tg; std::vector<GatherTask> gp, bg;
+    std::vector<SLaunch>& SS = c->slaunches;
+    const double* Fb = c->dL;                       /* forward sweep: L */
+    const double* Mb = LU ? c->dU : c->dL;          /* backward sweep: L' x, or U x through the U' panels */
+    struct Mark { int64_t t, g; };
+    auto mark = [&]( bool T ) { return Mark{ ( int64_t )( T ? tt.size() : tv.size() ), ( int64_t )tg.size() }; };
+    auto add_task = [&]( const SvTask& x, bool T ) {
+      if ( x.N <= 0 || x.K <= 0 ) return;
+      const int id = ( int )tk.size(); tk.push_back( x );
+      if ( T ) for ( int o = 0; o < x.N; o += GT_COLS ) tt.push_back( { id, o } ); else for ( int o = 0; o < x.N; o += KC ) tv.push_back( { id, o } );
+      for ( int o = 0; o < x.N; o += 64 ) tg.push_back( { id, o } );
+    };
+    auto close = [&]( int kind, int d, const Mark& m0, bool T ) {
+      const int64_t nt = ( int64_t )( T ? tt.size() : tv.size() ) - m0.t, ng = ( int64_t )tg.size() - m0.g;
+      if ( nt > 0 ) SS.push_back( { kind, d, 0, 0, m0.t, nt, m0.g, ng } );
+    };
+    for ( int d = S->maxdepth; d >= 0; d-- ) {
+      const std::vector<int>& lv = levels[d];
+      const int wsel = 2 + ( d & 1 );
+      if ( c->level_w[d] > 0 ) SS.push_back( { SK_FWD_ZERO_W, d, 0, c->level_w[d], 0, 0, 0, 0 } );
+      { const int64_t g0 = ( int64_t )gp.size();
+        for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
+          if ( any ) for ( int lo = 0; lo < meta[s].f; lo += GATHER_ROWS ) gp.push_back( { s, lo, std::min( meta[s].f, lo + GATHER_ROWS ) } ); }
+        if ( ( int64_t )gp.size() > g0 ) SS.push_back( { SK_FWD_GATHER, d, g0, ( int64_t )gp.size() - g0, 0, 0, 0, 0 } ); }
+      int nblk = 0; for ( int s : lv ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      for ( int t = 0; t < nblk; t++ ) {
+        Mark m0 = mark( false );
+        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          SvTask x; x.M = c->dSinvF + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 1; x.mode = 1;
+          x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0 + j0; add_task( x, false ); }
+        close( SK_FWD_TRI, d, m0, false );
+        m0 = mark( false );
+        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          SvTask x; x.ld = m.ld; x.K = nb; x.tri = 0; x.mode = 0; x.vsel = 1; x.voff = m.c0 + j0;
+          x.M = Fb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.N = m.k - j0 - nb; x.dsel = 0; x.doff = m.c0 + j0 + nb; add_task( x, false );      /* pivot rows below the block */
+          x.M = Fb + m.lptr + m.k + ( int64_t )j0 * m.ld; x.N = m.f - m.k; x.dsel = wsel; x.doff = m.wptr; add_task( x, false ); }                     /* update rows */
+        close( SK_FWD_UPD, d, m0, false );
       }
-      if ( ( int64_t )sb.size() == b0 ) continue;
-      c->max_part_rows = std::max( c->max_part_rows, prow );
-      c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
-      SS.push_back( { SK_FWD_STEP, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )ft.size() - t0, d } );
     }
-  }
-  for ( int d = 0; d <= S->maxdepth; d++ ) {
-    const std::vector<int>& lv = levels[d];
-    int maxk = 0; for ( int s : lv ) maxk = std::max( maxk, meta[s].k );
-    const int nblk = ( maxk + SB - 1 ) / SB;
-    /* step nblk: the update rows below the pivots (x gathered from the ancestors); steps nblk-1 .. 1: pivot block t feeds the columns before it */
-    for ( int t = nblk; t >= 1; t-- ) {
-      const int64_t b0 = ( int64_t )sb.size(), t0 = ( int64_t )bt.size(); int64_t prow = 0;
-      for ( int s : lv ) {
-        const SnMeta& m = meta[s];
-        const int nbs = ( m.k + SB - 1 ) / SB;
-        SolveBlk x; x.sn = s;
-        int cfirst = 0;
-        if ( t == nblk ) {
-          x.j0 = m.k; x.nb = m.f - m.k; x.la_j0 = ( nbs - 1 ) * SB; x.la_nb = m.k - x.la_j0; x.la_inv = m.sinv + ( int64_t )( nbs - 1 ) * SB * SB;
-          if ( x.nb == 0 ) cfirst = x.la_j0;      /* nothing to subtract: only the tiles that finish the last block */
-        } else {
-          if ( t >= nbs ) continue;
-          x.j0 = t * SB; x.nb = std::min( SB, m.k - x.j0 ); x.la_j0 = x.j0 - SB; x.la_nb = SB; x.la_inv = m.sinv + ( int64_t )( t - 1 ) * SB * SB;
-        }
-        x.la_tiles = ( x.la_nb + BT_COLS - 1 ) / BT_COLS;
-        x.la_part = prow; prow += ( int64_t )x.la_tiles * x.la_nb;
-        const int climit = std::min( x.j0, m.k );
-        const int id = ( int )( sb.size() - b0 ); sb.push_back( x );
-        for ( int c0 = cfirst; c0 < climit; c0 += BT_COLS ) bt.push_back( { id, c0 } );
+    for ( int d = 0; d <= S->maxdepth; d++ ) {
+      const std::vector<int>& lv = levels[d];
+      const int wsel = 2 + ( d & 1 );
+      { const int64_t g0 = ( int64_t )bg.size();
+        for ( int s : lv ) { const int u = meta[s].f - meta[s].k; for ( int lo = 0; lo < u; lo += GATHER_ROWS ) bg.push_back( { s, lo, std::min( u, lo + GATHER_ROWS ) } ); }
+        if ( ( int64_t )bg.size() > g0 ) SS.push_back( { SK_BWD_GATHER, d, g0, ( int64_t )bg.size() - g0, 0, 0, 0, 0 } ); }
+      { Mark m0 = mark( true );
+        for ( int s : lv ) { const SnMeta& m = meta[s];
+          SvTask x; x.M = Mb + m.lptr + m.k; x.ld = m.ld; x.K = m.f - m.k; x.N = m.k; x.tri = 0; x.mode = 0; x.vsel = wsel; x.voff = m.wptr; x.dsel = 1; x.doff = m.c0; add_task( x, true ); }
+        close( SK_BWD_UPD, d, m0, true ); }
+      int nblk = 0; for ( int s : lv ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      for ( int t = nblk - 1; t >= 0; t-- ) {
+        Mark m0 = mark( false );
+        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          SvTask x; x.M = c->dSinvB + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 2; x.mode = 1;
+          x.vsel = 1; x.voff = m.c0 + j0; x.dsel = 0; x.doff = m.c0 + j0; add_task( x, false ); }
+        close( SK_BWD_TRI, d, m0, false );
+        if ( t == 0 ) break;
+        m0 = mark( true );
+        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          SvTask x; x.M = Mb + m.lptr + j0; x.ld = m.ld; x.K = nb; x.N = j0; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0; add_task( x, true ); }
+        close( SK_BWD_UPD, d, m0, true );
       }
-      if ( ( int64_t )sb.size() == b0 ) continue;
-      c->max_part_rows = std::max( c->max_part_rows, prow );
-      c->max_blocks_per_launch = std::max<int64_t>( c->max_blocks_per_launch, ( int64_t )sb.size() - b0 );
-      SS.push_back( { SK_BWD_STEP, b0, ( int64_t )sb.size() - b0, t0, ( int64_t )bt.size() - t0, d } );
     }
+    if ( c->sv_tasks.upload( tk ) || c->sv_tiles_v.upload( tv ) || c->sv_tiles_t.upload( tt ) || c->sv_tiles_g.upload( tg ) || c->gather_tasks.upload( gp ) || c->bgather_tasks.upload( bg ) ) return B200_ERR_CUDA;
+    if ( !c->dry && tk.size() ) CK( cudaMalloc( &c->dSvGemm, tk.size() * sizeof( SvGemm ) ) );
+    c->sv_gemm_p = 0;
   }
-  if ( c->sblk.upload( sb ) || c->fwd_tiles.upload( ft ) || c->bwd_tiles.upload( bt ) || c->gather_tasks.upload( gp ) ) return B200_ERR_CUDA;
   c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
-                     c->asm_tasks.bytes() + c->sblk.bytes() + c->fwd_tiles.bytes() + c->bwd_tiles.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
-  if ( !c->dry ) CK( cudaStreamSynchronize( c->stream ) );
+                     c->asm_tasks.bytes() + c->sv_tasks.bytes() * 2 + c->sv_tiles_v.bytes() + c->sv_tiles_t.bytes() + c->sv_tiles_g.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
   return B200_OK;
 }
 
@@ -903,56 +919,53 @@ extern "C" int b200_factor_host( b200_ctx_t* c, const double* vals ) {
 }
 
 /* -------------------------------------------------------------- solve */
+static inline int solve_pitch( int p ) { return p <= 4 ? p : ( p + 1 ) & ~1; }     /* tensor path: even pitch = 16-byte aligned rows for the bulk copies */
 static int ensure_solve_ws( b200_ctx* c, int p ) {
   if ( p <= c->solve_p_cap ) return B200_OK;
-  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dTickets ); cudaFree( c->dPart ); c->dPart = nullptr;
-  c->dY = c->dW[0] = c->dW[1] = c->dR = c->dD = c->dZ = nullptr; c->dTickets = nullptr; c->solve_p_cap = 0;
-  CK( cudaMalloc( &c->dY, ( size_t )c->n * p * 8 ) );
+  cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ );
+  c->dY = c->dW[0] = c->dW[1] = c->dR = c->dD = c->dZ = nullptr; c->solve_p_cap = 0; c->sv_gemm_p = 0;
+  const size_t pitch = ( size_t )solve_pitch( p ) + 2;      /* capacity for any p' <= p */
+  CK( cudaMalloc( &c->dY, ( ( size_t )c->n + 2 ) * pitch * 8 ) ); CK( cudaMalloc( &c->dZ, ( ( size_t )c->n + 2 ) * pitch * 8 ) );
   CK( cudaMalloc( &c->dR, ( size_t )c->n * p * 8 ) ); CK( cudaMalloc( &c->dD, ( size_t )c->n * p * 8 ) );
-  for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dW[a], ( size_t )std::max<int64_t>( c->w_rows[a], 1 ) * p * 8 ) );
-  const int pchunks = p;     /* upper bound for either chunking (1 or 8 right-hand sides per CTA) */
-  CK( cudaMalloc( &c->dPart, ( size_t )std::max<int64_t>( c->max_part_rows, 1 ) * p * 8 ) );
-  CK( cudaMalloc( &c->dZ, ( size_t )c->n * p * 8 ) );
-  { const size_t tb = ( size_t )std::max<int64_t>( c->max_blocks_per_launch, 1 ) * pchunks * sizeof( unsigned int ); CK( cudaMalloc( &c->dTickets, tb ) ); CK( cudaMemsetAsync( c->dTickets, 0, tb, c->stream ) ); }
+  for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dW[a], ( ( size_t )std::max<int64_t>( c->w_rows[a], 1 ) + 2 ) * pitch * 8 ) );
   c->solve_p_cap = p;
   return B200_OK;
 }
 
 /* one pair of sweeps: d_x = (LL')^-1 d_b  (or (LU)^-1), launches counted into nl */
 static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64_t& nl ) {
-  const bool LU = c->kind == B200_KIND_LU;
   cudaStream_t st = c->stream;
   const int n = c->n;
-  const int gchunks = ( p + PC - 1 ) / PC;                 /* gather: 8 right-hand sides per CTA */
-  const bool one = p == 1;                                 /* sweep kernels: 1 or 8 right-hand sides per CTA */
-  const int pchunks = one ? 1 : ( p + 7 ) / 8;
-  const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * p + 255 ) / 256, 148 * 32 );
-  permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, c->dY );
+  const int pitch = solve_pitch( p );
+  const bool tensor = p > 4;
+  const int pct = p <= 1 ? 1 : p <= 2 ? 2 : 4;
+  const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * pitch + 255 ) / 256, 148 * 32 );
+  SvBases B; B.b[0] = c->dY; B.b[1] = c->dZ; B.b[2] = c->dW[0]; B.b[3] = c->dW[1];
+  if ( tensor && c->sv_gemm_p != p && c->sv_tasks.n ) {      /* the task list is the same for every p; only the vector addresses / pitch / M change */
+    sv_expand_kernel<<<( unsigned )( ( c->sv_tasks.n + 255 ) / 256 ), 256, 0, st>>>( c->sv_tasks.d, ( int64_t )c->sv_tasks.n, B, p, pitch, c->dSvGemm );
+    c->sv_gemm_p = p; nl++;
+  }
+  permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, pitch, c->dY );
   nl += 2;
-  const int64_t ldw[2] = { std::max<int64_t>( c->w_rows[0], 1 ), std::max<int64_t>( c->w_rows[1], 1 ) };
-  const double* Mb = LU ? c->dU : c->dL;
+  const unsigned gy = ( unsigned )( ( p + 63 ) / 64 );
   for ( const SLaunch& l : c->slaunches ) {
     const int a = l.depth & 1, ac = ( l.depth + 1 ) & 1;
     if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
     switch ( l.kind ) {
-      case SK_FWD_ZERO_W:
-        CK( cudaMemset2DAsync( c->dW[a], ( size_t )ldw[a] * 8, 0, ( size_t )l.count * 8, ( size_t )p, st ) );
+      case SK_FWD_ZERO_W: CK( cudaMemsetAsync( c->dW[a], 0, ( size_t )l.count * pitch * 8, st ) ); break;
+      case SK_FWD_GATHER: fwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->gather_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, pitch, c->dW[a], c->dW[ac] ); break;
+      case SK_BWD_GATHER: bwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->bgather_tasks.d + l.first, c->sn.d, c->rowidx.d, c->dY, pitch, c->dW[a] ); break;
+      case SK_FWD_TRI: case SK_FWD_UPD: case SK_BWD_TRI:
+        if ( tensor ) gemm_solve_dmma_kernel<false><<<dim3( ( unsigned )l.ng, gy ), 288, SVG_SMEM_NT, st>>>( c->dSvGemm, c->sv_tiles_g.d + l.g0, c->dZeros );
+        else if ( pct == 1 ) sv_gemv_kernel<1><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
+        else if ( pct == 2 ) sv_gemv_kernel<2><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
+        else sv_gemv_kernel<4><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
         break;
-      case SK_FWD_GATHER:
-        fwd_gather_kernel<<<dim3( ( unsigned )l.count, gchunks ), 256, 0, st>>>( c->gather_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, n, p, c->dW[a], ldw[a], c->dW[ac], ldw[ac] );
-        break;
-      case SK_FWD_FIRST:
-        if ( one ) solve_first_block_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dSinvF, c->dY, c->dZ, n, p, c->dPart, c->dTickets );
-        else solve_first_block_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dSinvF, c->dY, c->dZ, n, p, c->dPart, c->dTickets );
-        break;
-      case SK_FWD_STEP:
-        if ( one ) solve_fwd_step_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, n, p, c->dW[a], ldw[a], c->dPart, c->dTickets );
-        else solve_fwd_step_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->fwd_tiles.d + l.first_tile, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, n, p, c->dW[a], ldw[a], c->dPart, c->dTickets );
-        break;
-      case SK_BWD_STEP:
-        if ( l.ntiles == 0 ) break;
-        if ( one ) solve_bwd_step_kernel<1><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dZ, n, p, c->dPart, c->dTickets );
-        else solve_bwd_step_kernel<8><<<dim3( ( unsigned )l.ntiles, pchunks ), SB, 0, st>>>( c->sblk.d + l.first, c->bwd_tiles.d + l.first_tile, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dZ, n, p, c->dPart, c->dTickets );
+      case SK_BWD_UPD:
+        if ( tensor ) gemm_solve_dmma_kernel<true><<<dim3( ( unsigned )l.ng, gy ), 288, SVG_SMEM_BT, st>>>( c->dSvGemm, c->sv_tiles_g.d + l.g0, c->dZeros );
+        else if ( pct == 1 ) sv_gemvT_kernel<1><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
+        else if ( pct == 2 ) sv_gemvT_kernel<2><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
+        else sv_gemvT_kernel<4><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
         break;
     }
     nl++;
@@ -960,10 +973,10 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
       CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) );
       float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->sprof_ms[l.kind] += ms; c->sprof_n[l.kind]++;
       static const bool trace_all = getenv( "B200_TRACE_ALL" ) != nullptr;
-      if ( trace_all ) fprintf( stderr, "slaunch kind=%d depth=%d blocks=%lld tiles=%lld ms=%.4f\n", l.kind, l.depth, ( long long )l.count, ( long long )l.ntiles, ms );
+      if ( trace_all ) fprintf( stderr, "slaunch kind=%d depth=%d tiles=%lld gtiles=%lld ms=%.4f\n", l.kind, l.depth, ( long long )l.nt, ( long long )l.ng, ms );
     }
   }
-  permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dZ, c->perm.d, n, p, d_x );
+  permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dY, c->perm.d, n, p, pitch, d_x );
   return B200_OK;
 }
 
@@ -1067,7 +1080,7 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   std::string s;
   char line[256];
   for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
-  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_first", "solve_fwd_step", "solve_bwd_step" };
+  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_tri", "solve_fwd_upd", "solve_bwd_gather", "solve_bwd_upd", "solve_bwd_tri" };
   for ( int k = 0; k < SK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", sname[k], ( long long )c->sprof_n[k], c->sprof_ms[k] ); s += line; }
   { float t0 = 0; if ( !c->lvl_ev.empty() ) cudaEventElapsedTime( &t0, c->ev0, c->lvl_ev[0] ); snprintf( line, sizeof( line ), "levels_ms(deepest first; prologue %.2f):", t0 ); s += line;
     for ( float v : c->lvl_ms ) { snprintf( line, sizeof( line ), " %.2f", v ); s += line; } s += "\n"; }

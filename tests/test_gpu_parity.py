@@ -191,6 +191,34 @@ def test_sweeps_over_several_256_column_blocks_and_rhs_chunks(mc, kind):
     s.close()
 
 
+@pytest.mark.parametrize("kind", ["cholesky", "lu"])
+def test_wide_solve_blocks_same_bits_for_every_batch(mc, kind, monkeypatch):
+    """the big fronts use 1024-column solve blocks (B200_SOLVE_WIDE_MIN forces them on a small system): FMA kernels (p <= 4) and the
+    tensor path (p >= 5) follow one canonical arithmetic, so a column has the same bits in every batch"""
+    import scipy.sparse.linalg as sla
+    monkeypatch.setenv("B200_SOLVE_WIDE_MIN", "512")
+    if kind == "cholesky":
+        n, cp, ri, v = stencils.poisson3d_upper(34, 33, 35); A = stencils.to_scipy(n, cp, ri, v, True); k = mc.KIND_CHOLESKY
+    else:
+        n, cp, ri, v = stencils.convdiff27_full(36, 34, 35); A = stencils.to_scipy(n, cp, ri, v, False); k = mc.KIND_LU
+    s = mc.Solver(); S = s.analyze(n, cp, ri, k)
+    st = mc.sym_array(s.S, "sn_start", S.ns + 1, np.int32)
+    assert np.diff(st).max() > 1024 + 64, "the case must have a supernode with a full wide block and a ragged second one"
+    s.L.b200_set_refinement(s.ctx, 0)
+    assert s.factor(v) == 0
+    rng = np.random.default_rng(11); B = rng.standard_normal((n, 70))
+    X = s.solve(B)                                           # tensor path, two 64-wide slices of right-hand sides
+    for c in (0, 63, 64, 69):
+        assert np.array_equal(X[:, c], s.solve(B[:, c].copy()))          # FMA path, p = 1
+    assert np.array_equal(X[:, 3:6], s.solve(B[:, 3:6].copy()))          # FMA path, p = 3
+    assert np.array_equal(X[:, 10:21], s.solve(B[:, 10:21].copy()))      # tensor path, odd p
+    Xr = sla.splu(A.tocsc()).solve(B)
+    assert np.abs(X - Xr).max() <= 1e-10 * np.abs(Xr).max()
+    for c in range(0, 70, 7):
+        assert backward_error(A, X[:, c], B[:, c]) <= 1e-12
+    s.close()
+
+
 def test_not_positive_definite_is_reported_not_hidden(mc, golden):
     Ad = read_mm_dense(f"{golden}/sym.mm")
     U = sp.triu(sp.csc_matrix(Ad)).tocsc(); U.sort_indices()
