@@ -941,10 +941,12 @@ __global__ void permute_out_kernel( const double* __restrict__ y, const int* __r
 constexpr int GATHER_ROWS = 2048;
 struct GatherTask { int parent; int lo; int hi; };
 __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const GatherTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const int* __restrict__ child_list,
-                                                            const int* __restrict__ relidx, double* __restrict__ y, int pitch,
+                                                            const int* __restrict__ relidx, double* __restrict__ y, int pitch, int tqs,
                                                             double* __restrict__ w_parent, const double* __restrict__ w_child ) {
   const GatherTask t = tasks[blockIdx.x];
   const SnMeta P = sn[t.parent];
+  /* thread = (row slot, right-hand-side slot): 2^tqs consecutive threads walk the right-hand sides of one row (coalesced) */
+  const int TQ = 1 << tqs, tq = threadIdx.x & ( TQ - 1 ), ti = threadIdx.x >> tqs, tr = blockDim.x >> tqs;
   for ( int ci = P.child_begin; ci < P.child_end; ci++ ) {
     const SnMeta C = sn[child_list[ci]];
     const int uc = C.f - C.k;
@@ -954,135 +956,150 @@ __global__ void __launch_bounds__( 256 ) fwd_gather_kernel( const GatherTask* __
       { int x = 0, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.lo ) x = m + 1; else z = m; } a = x; }
       { int x = a, z = uc; while ( x < z ) { const int m = ( x + z ) >> 1; if ( rel[m] < t.hi ) x = m + 1; else z = m; } b = x; }
     }
-    const int64_t tot = ( int64_t )( b - a ) * pitch;
-    for ( int64_t e = threadIdx.x; e < tot; e += blockDim.x ) {
-      const int i = a + ( int )( e / pitch ), q = ( int )( e % pitch );
+    for ( int i = a + ti; i < b; i += tr ) {
       const int d = rel[i];
-      const double v = w_child[( C.wptr + i ) * pitch + q];
-      if ( d < P.k ) y[( int64_t )( P.c0 + d ) * pitch + q] += v;
-      else w_parent[( P.wptr + ( d - P.k ) ) * pitch + q] += v;
+      const double* src = w_child + ( C.wptr + i ) * pitch;
+      double* dst = d < P.k ? y + ( int64_t )( P.c0 + d ) * pitch : w_parent + ( P.wptr + ( d - P.k ) ) * pitch;
+      for ( int q = tq; q < pitch; q += TQ ) dst[q] += src[q];
     }
     __syncthreads();
   }
 }
 /* backward: xg[update row i of s] = x[global row], for every supernode of a level (x of the ancestors is final) */
 __global__ void __launch_bounds__( 256 ) bwd_gather_kernel( const GatherTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const int* __restrict__ rowidx,
-                                                            const double* __restrict__ x, int pitch, double* __restrict__ xg ) {
+                                                            const double* __restrict__ x, int pitch, int tqs, double* __restrict__ xg ) {
   const GatherTask t = tasks[blockIdx.x];
   const SnMeta S = sn[t.parent];
   const int* ri = rowidx + S.rowptr + S.k;
-  const int64_t tot = ( int64_t )( t.hi - t.lo ) * pitch;
-  for ( int64_t e = threadIdx.x; e < tot; e += blockDim.x ) {
-    const int i = t.lo + ( int )( e / pitch ), q = ( int )( e % pitch );
-    xg[( S.wptr + i ) * pitch + q] = x[( int64_t )ri[i] * pitch + q];
+  const int TQ = 1 << tqs, tq = threadIdx.x & ( TQ - 1 ), ti = threadIdx.x >> tqs, tr = blockDim.x >> tqs;
+  for ( int i = t.lo + ti; i < t.hi; i += tr ) {
+    const double* src = x + ( int64_t )ri[i] * pitch;
+    double* dst = xg + ( S.wptr + i ) * pitch;
+    for ( int q = tq; q < pitch; q += TQ ) dst[q] = src[q];
   }
 }
 
-/* dest (-)= M v, outputs = rows of M (M is N x K column-major): 64 output rows per CTA, thread = (row, one of 4 chunk lanes).
- * Round j: chunk lane g forms the chain of chunk 4j+g; the chunk sums are then subtracted in chunk order by lane 0.
- * Lanes of a warp run down the rows of a column of M: coalesced. */
+/* dest (-)= M v, outputs = rows of M (M is N x K column-major, K <= SB_WIDE): GV_ROWS = 32 output rows per CTA, thread = (row, one of 8
+ * chunk lanes).  Chunk lane g forms the chains of chunks g, g+8, ... -- 16 independent coalesced loads in flight per thread (a warp runs
+ * down 32 rows of a column of M), then the 16 FMAs of the chain; the chunk sums are parked in shared memory and subtracted in chunk
+ * order by lane 0. */
+constexpr int GV_ROWS = 32;
+constexpr int SVG_MAXCH = SB_WIDE / KC;
+template <int PCT> constexpr int sv_gemv_smem() { return ( SB_WIDE + SVG_MAXCH * GV_ROWS ) * PCT * 8; }
+/* keeps the 16 loads of a batch together: every value must have arrived before the first FMA of the chain issues */
+__device__ __forceinline__ void pin8( double& a, double& b, double& c, double& d, double& e, double& f, double& g, double& h ) {
+  asm volatile( "" : "+d"( a ), "+d"( b ), "+d"( c ), "+d"( d ), "+d"( e ), "+d"( f ), "+d"( g ), "+d"( h ) );
+}
 template <int PCT>
 __global__ void __launch_bounds__( 256 ) sv_gemv_kernel( const SvTask* __restrict__ tasks, const SvTile* __restrict__ tiles, SvBases B, int p, int pitch ) {
-  __shared__ double vs[4 * KC][PCT];
-  __shared__ double part[3][KC][PCT];
+  extern __shared__ double dsm[];
+  double ( *vs )[PCT] = reinterpret_cast<double ( * )[PCT]>( dsm );                                          /* [K][PCT]            */
+  double ( *part )[GV_ROWS][PCT] = reinterpret_cast<double ( * )[GV_ROWS][PCT]>( dsm + SB_WIDE * PCT );       /* [chunk][row][PCT]   */
   const SvTile tl = tiles[blockIdx.x];
   const SvTask t = tasks[tl.task];
   const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
-  const int tid = threadIdx.x, r = tid & ( KC - 1 ), g = tid >> 6;
+  const int tid = threadIdx.x, r = tid & ( GV_ROWS - 1 ), g = tid >> 5;
   const int row = tl.o0 + r;
   const bool live = row < t.N;
   const double* v = B.b[t.vsel] + t.voff * pitch + pc0;
   double* dest = B.b[t.dsel] + ( t.doff + row ) * pitch + pc0;
-  /* reduction window of this tile: lower triangular -> k < o0 + 64, upper -> k >= o0 (o0 is a multiple of 64: whole chunks) */
-  const int k_lo = t.tri == 2 ? tl.o0 : 0, k_hi = t.tri == 1 ? min( t.K, tl.o0 + KC ) : t.K;
+  /* reduction window of this tile in whole chunks: lower triangular -> chunks up to the one holding the tile's last row, upper -> from the one holding its first */
+  const int k_lo = t.tri == 2 ? ( tl.o0 & ~( KC - 1 ) ) : 0, k_hi = t.tri == 1 ? min( t.K, ( ( tl.o0 + GV_ROWS - 1 ) | ( KC - 1 ) ) + 1 ) : t.K;
+  for ( int e = tid; e < ( k_hi - k_lo ) * PCT; e += 256 ) { const int kk = e / PCT, q = e % PCT; vs[kk][q] = q < pcn ? v[( int64_t )( k_lo + kk ) * pitch + q] : 0.0; }
   double cr[PCT];
 #pragma unroll
   for ( int q = 0; q < PCT; q++ ) cr[q] = ( t.mode == 0 && live && g == 0 && q < pcn ) ? dest[q] : 0.0;
-  const double* Mr = t.M + row;
-  for ( int kb = k_lo; kb < k_hi; kb += 4 * KC ) {
-    __syncthreads();
-    for ( int e = tid; e < 4 * KC * PCT; e += 256 ) { const int kk = e / PCT, q = e % PCT; vs[kk][q] = ( kb + kk < k_hi && q < pcn ) ? v[( int64_t )( kb + kk ) * pitch + q] : 0.0; }
-    __syncthreads();
-    const int k0 = kb + g * KC, kn = min( KC, k_hi - k0 );      /* my chunk: [k0, k0 + kn) */
+  __syncthreads();
+  const int nch = ( k_hi - k_lo + KC - 1 ) / KC;
+  const int64_t ldm = t.ld;
+  for ( int ch = g; ch < nch; ch += 8 ) {
+    const int k0 = k_lo + ch * KC, kn = min( KC, k_hi - k0 );
     double acc[PCT];
 #pragma unroll
     for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-    if ( kn > 0 && live ) {
-      const double* Mc = Mr + ( int64_t )k0 * t.ld;
-      for ( int c = 0; c < kn; c += 16 ) {
-        double mv[16];
+    if ( live ) {
+      const double* Mc = t.M + row + ( int64_t )k0 * ldm;
+      const double ( *vc )[PCT] = vs + ch * KC;
+      if ( kn == KC ) {
+#pragma unroll 1
+        for ( int h = 0; h < KC; h += 16 ) {
+          double mv[16];
 #pragma unroll
-        for ( int i = 0; i < 16; i++ ) mv[i] = ( c + i < kn ) ? Mc[( int64_t )( c + i ) * t.ld] : 0.0;      /* 16 independent coalesced loads in flight */
+          for ( int i = 0; i < 16; i++ ) mv[i] = __ldg( Mc + ( h + i ) * ldm );
+          pin8( mv[0], mv[1], mv[2], mv[3], mv[4], mv[5], mv[6], mv[7] ); pin8( mv[8], mv[9], mv[10], mv[11], mv[12], mv[13], mv[14], mv[15] );
 #pragma unroll
-        for ( int i = 0; i < 16; i++ ) {
+          for ( int i = 0; i < 16; i++ ) {
 #pragma unroll
-          for ( int q = 0; q < PCT; q++ ) acc[q] = fma( mv[i], vs[g * KC + c + i][q], acc[q] );              /* beyond kn: mv = 0 and vs = 0 */
+            for ( int q = 0; q < PCT; q++ ) acc[q] = fma( mv[i], vc[h + i][q], acc[q] );
+          }
+        }
+      } else {
+        for ( int i = 0; i < kn; i++ ) {
+          const double m = __ldg( Mc + i * ldm );
+#pragma unroll
+          for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, vc[i][q], acc[q] );
         }
       }
     }
-    if ( g > 0 ) {
 #pragma unroll
-      for ( int q = 0; q < PCT; q++ ) part[g - 1][r][q] = acc[q];
-    }
-    __syncthreads();
-    if ( g == 0 ) {
-#pragma unroll
-      for ( int q = 0; q < PCT; q++ ) {
-        double c_ = cr[q] - acc[q];
-        if ( kb + KC < k_hi ) c_ -= part[0][r][q];
-        if ( kb + 2 * KC < k_hi ) c_ -= part[1][r][q];
-        if ( kb + 3 * KC < k_hi ) c_ -= part[2][r][q];
-        cr[q] = c_;
-      }
-    }
+    for ( int q = 0; q < PCT; q++ ) part[ch][r][q] = acc[q];
   }
+  __syncthreads();
   if ( g == 0 && live ) {
+    for ( int ch = 0; ch < nch; ch++ ) {
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) cr[q] -= part[ch][r][q];
+    }
 #pragma unroll
     for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) dest[q] = t.mode == 0 ? cr[q] : -cr[q];
   }
 }
 
-/* dest -= M' v, outputs = columns of M (M is K x N column-major, the reduction runs down the contiguous rows): 32 output columns per
- * CTA, 4 per warp.  Per chunk of 64 rows a warp brings its 64 x 4 slab in with coalesced loads (the next chunk is already in
- * flight), parks it in shared memory, and lanes 0..3 run the canonical chains -- the FMA work is 1/8 of a percent of the pipe,
- * the kernel streams. */
-constexpr int GT_COLS = 32;
+/* dest -= M' v, outputs = columns of M (M is K x N column-major, the reduction runs down the contiguous rows): 64 output columns per
+ * CTA of 4 warps, 16 per warp.  Per chunk of 64 rows a warp brings its 64 x 16 slab in with coalesced loads (the next chunk is
+ * already in flight in registers), parks it in shared memory, and lanes 0..15 run one canonical chain each -- the FMA work is a
+ * fraction of a percent of the pipe, the kernel streams. */
+constexpr int GT_COLS = 64;
 constexpr int GT_XS = 512;      /* rows of v staged per pass */
+template <int PCT> constexpr int sv_gemvT_smem() { return ( GT_XS * PCT + 4 * 16 * ( KC + 1 ) ) * 8; }
 template <int PCT>
-__global__ void __launch_bounds__( 256 ) sv_gemvT_kernel( const SvTask* __restrict__ tasks, const SvTile* __restrict__ tiles, SvBases B, int p, int pitch ) {
-  __shared__ double xs[GT_XS][PCT];
-  __shared__ double slab[8][4][KC + 1];
+__global__ void __launch_bounds__( 128 ) sv_gemvT_kernel( const SvTask* __restrict__ tasks, const SvTile* __restrict__ tiles, SvBases B, int p, int pitch ) {
+  extern __shared__ double dsm[];
+  double ( *xs )[PCT] = reinterpret_cast<double ( * )[PCT]>( dsm );                                                   /* [GT_XS][PCT]      */
+  double ( *slab )[16][KC + 1] = reinterpret_cast<double ( * )[16][KC + 1]>( dsm + GT_XS * PCT );                      /* [warp][col][row]  */
   const SvTile tl = tiles[blockIdx.x];
   const SvTask t = tasks[tl.task];
   const int pc0 = blockIdx.y * PCT, pcn = min( PCT, p - pc0 );
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cbase = tl.o0 + warp * 4;
+  const int cbase = tl.o0 + warp * 16;
   const double* v = B.b[t.vsel] + t.voff * pitch + pc0;
-  const int mycol = cbase + ( lane & 3 );
+  const int mycol = cbase + ( lane & 15 );
   double* dest = B.b[t.dsel] + ( t.doff + mycol ) * pitch + pc0;
-  const bool owner = lane < 4 && mycol < t.N;
+  const bool owner = lane < 16 && mycol < t.N;
   double cr[PCT];
 #pragma unroll
   for ( int q = 0; q < PCT; q++ ) cr[q] = ( owner && q < pcn ) ? dest[q] : 0.0;
-  const int ncol = max( 0, min( 4, t.N - cbase ) );
-  const double* Mw = t.M + ( int64_t )cbase * t.ld;
-  double pre[8];
+  const int ncol = max( 0, min( 16, t.N - cbase ) );
+  const int64_t ldm = t.ld;
+  const double* Mw = t.M + ( int64_t )cbase * ldm + lane;
+  double pre[32];
   auto fetch = [&]( int k0 ) {
+    const bool r0 = k0 + lane < t.K, r1 = k0 + lane + 32 < t.K;
 #pragma unroll
-    for ( int j = 0; j < 4; j++ ) {
-#pragma unroll
-      for ( int h = 0; h < 2; h++ ) { const int k = k0 + lane + 32 * h; pre[2 * j + h] = ( j < ncol && k < t.K ) ? Mw[k + ( int64_t )j * t.ld] : 0.0; }
+    for ( int j = 0; j < 16; j++ ) {
+      pre[2 * j] = ( j < ncol && r0 ) ? __ldg( Mw + k0 + j * ldm ) : 0.0;
+      pre[2 * j + 1] = ( j < ncol && r1 ) ? __ldg( Mw + k0 + 32 + j * ldm ) : 0.0;
     }
   };
   if ( t.K > 0 ) fetch( 0 );
   for ( int kb = 0; kb < t.K; kb += GT_XS ) {
     const int rows = min( GT_XS, t.K - kb );
     __syncthreads();
-    for ( int e = tid; e < rows * PCT; e += 256 ) { const int kk = e / PCT, q = e % PCT; xs[kk][q] = q < pcn ? v[( int64_t )( kb + kk ) * pitch + q] : 0.0; }
+    for ( int e = tid; e < rows * PCT; e += 128 ) { const int kk = e / PCT, q = e % PCT; xs[kk][q] = q < pcn ? v[( int64_t )( kb + kk ) * pitch + q] : 0.0; }
     __syncthreads();
     for ( int k0 = 0; k0 < rows; k0 += KC ) {
 #pragma unroll
-      for ( int j = 0; j < 4; j++ ) { slab[warp][j][lane] = pre[2 * j]; slab[warp][j][lane + 32] = pre[2 * j + 1]; }
+      for ( int j = 0; j < 16; j++ ) { slab[warp][j][lane] = pre[2 * j]; slab[warp][j][lane + 32] = pre[2 * j + 1]; }
       if ( kb + k0 + KC < t.K ) fetch( kb + k0 + KC );
       __syncwarp();
       if ( owner ) {
@@ -1090,11 +1107,20 @@ __global__ void __launch_bounds__( 256 ) sv_gemvT_kernel( const SvTask* __restri
         double acc[PCT];
 #pragma unroll
         for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
-        const double* sl = slab[warp][lane & 3];
-        for ( int i = 0; i < kn; i++ ) {
-          const double m = sl[i];
+        const double* sl = slab[warp][lane & 15];
+        if ( kn == KC ) {
+#pragma unroll 16
+          for ( int i = 0; i < KC; i++ ) {
+            const double m = sl[i];
 #pragma unroll
-          for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, xs[k0 + i][q], acc[q] );
+            for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, xs[k0 + i][q], acc[q] );
+          }
+        } else {
+          for ( int i = 0; i < kn; i++ ) {
+            const double m = sl[i];
+#pragma unroll
+            for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, xs[k0 + i][q], acc[q] );
+          }
         }
 #pragma unroll
         for ( int q = 0; q < PCT; q++ ) cr[q] -= acc[q];
@@ -1105,6 +1131,120 @@ __global__ void __launch_bounds__( 256 ) sv_gemvT_kernel( const SvTask* __restri
   if ( owner ) {
 #pragma unroll
     for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) dest[q] = cr[q];
+  }
+}
+
+/* ---- supernodes with at most KC pivot columns (one canonical chunk, one solve block): the whole supernode in one CTA per sweep.
+ * Nine tenths of the supernodes live here; through the generic task lists each of them would cost three launch-wide tiles.
+ * The arithmetic is the canonical one (single-chunk chains in ascending k), so the bits equal those of the generic kernels.
+ * forward : z = X y ;  w[update rows] -= L21 z
+ * backward: v = z - L21' x[ancestors] (chunks of 64 update rows, chain per chunk) ;  x = X' v                                  */
+constexpr int SVS_THREADS = 128;
+template <int PCT>
+__global__ void __launch_bounds__( SVS_THREADS ) sv_small_fwd_kernel( const int* __restrict__ sns, int pchunks, const SnMeta* __restrict__ sn, const double* __restrict__ L,
+                                                                     const double* __restrict__ sinvF, const double* __restrict__ Y, double* __restrict__ Z, double* __restrict__ W, int p, int pitch ) {
+  __shared__ double ys[KC][PCT];
+  __shared__ double zs[KC][PCT];
+  const SnMeta S = sn[sns[blockIdx.x / pchunks]];
+  const int pc0 = ( blockIdx.x % pchunks ) * PCT, pcn = min( PCT, p - pc0 );
+  const int k = S.k, u = S.f - k, tid = threadIdx.x;
+  const int64_t ldx = ( k + 1 ) & ~1;
+  for ( int e = tid; e < k * PCT; e += SVS_THREADS ) { const int c = e / PCT, q = e % PCT; ys[c][q] = q < pcn ? Y[( int64_t )( S.c0 + c ) * pitch + pc0 + q] : 0.0; }
+  __syncthreads();
+  if ( tid < k ) {
+    const double* Xr = sinvF + S.sinv + tid;
+    double acc[PCT];
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+    for ( int c = 0; c < k; c++ ) {
+      const double m = __ldg( Xr + c * ldx );
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, ys[c][q], acc[q] );
+    }
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) { const double z = -( 0.0 - acc[q] ); zs[tid][q] = z; if ( q < pcn ) Z[( int64_t )( S.c0 + tid ) * pitch + pc0 + q] = z; }
+  }
+  __syncthreads();
+  const double* Lp = L + S.lptr + k;
+  for ( int i = tid; i < u; i += SVS_THREADS ) {
+    double acc[PCT];
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+    const double* Lr = Lp + i;
+    int c = 0;
+    for ( ; c + 8 <= k; c += 8 ) {
+      double mv[8];
+#pragma unroll
+      for ( int j = 0; j < 8; j++ ) mv[j] = __ldg( Lr + ( int64_t )( c + j ) * S.ld );
+#pragma unroll
+      for ( int j = 0; j < 8; j++ ) {
+#pragma unroll
+        for ( int q = 0; q < PCT; q++ ) acc[q] = fma( mv[j], zs[c + j][q], acc[q] );
+      }
+    }
+    for ( ; c < k; c++ ) {
+      const double m = __ldg( Lr + ( int64_t )c * S.ld );
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, zs[c][q], acc[q] );
+    }
+    double* wp = W + ( S.wptr + i ) * pitch + pc0;
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) wp[q] -= acc[q];
+  }
+}
+
+template <int PCT>
+__global__ void __launch_bounds__( SVS_THREADS ) sv_small_bwd_kernel( const int* __restrict__ sns, int pchunks, const SnMeta* __restrict__ sn, const double* __restrict__ M,
+                                                                     const double* __restrict__ sinvB, const int* __restrict__ rowidx, double* __restrict__ Y, const double* __restrict__ Z, int p, int pitch ) {
+  __shared__ double slab[KC][KC + 1];     /* [col][row of the chunk] */
+  __shared__ double xs[KC][PCT];
+  __shared__ double vs[KC][PCT];
+  const SnMeta S = sn[sns[blockIdx.x / pchunks]];
+  const int pc0 = ( blockIdx.x % pchunks ) * PCT, pcn = min( PCT, p - pc0 );
+  const int k = S.k, u = S.f - k, tid = threadIdx.x;
+  const int64_t ldx = ( k + 1 ) & ~1;
+  const int* ri = rowidx + S.rowptr + k;
+  const double* Mp = M + S.lptr + k;
+  double cr[PCT];
+#pragma unroll
+  for ( int q = 0; q < PCT; q++ ) cr[q] = ( tid < k && q < pcn ) ? Z[( int64_t )( S.c0 + tid ) * pitch + pc0 + q] : 0.0;
+  for ( int k0 = 0; k0 < u; k0 += KC ) {
+    const int kn = min( KC, u - k0 );
+    __syncthreads();
+    for ( int e = tid; e < kn * PCT; e += SVS_THREADS ) { const int i = e / PCT, q = e % PCT; xs[i][q] = q < pcn ? Y[( int64_t )ri[k0 + i] * pitch + pc0 + q] : 0.0; }
+    for ( int e = tid; e < k * KC; e += SVS_THREADS ) { const int i = e & ( KC - 1 ), c = e >> 6; if ( i < kn ) slab[c][i] = __ldg( Mp + k0 + i + ( int64_t )c * S.ld ); }
+    __syncthreads();
+    if ( tid < k ) {
+      double acc[PCT];
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+      for ( int i = 0; i < kn; i++ ) {
+        const double m = slab[tid][i];
+#pragma unroll
+        for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, xs[i][q], acc[q] );
+      }
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) cr[q] -= acc[q];
+    }
+  }
+  __syncthreads();
+  if ( tid < k ) {
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) vs[tid][q] = cr[q];
+  }
+  __syncthreads();
+  if ( tid < k ) {
+    const double* Xr = sinvB + S.sinv + tid;
+    double acc[PCT];
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) acc[q] = 0.0;
+    for ( int c = 0; c < k; c++ ) {
+      const double m = __ldg( Xr + c * ldx );
+#pragma unroll
+      for ( int q = 0; q < PCT; q++ ) acc[q] = fma( m, vs[c][q], acc[q] );
+    }
+#pragma unroll
+    for ( int q = 0; q < PCT; q++ ) if ( q < pcn ) Y[( int64_t )( S.c0 + tid ) * pitch + pc0 + q] = -( 0.0 - acc[q] );
   }
 }
 
@@ -1125,8 +1265,8 @@ __global__ void sv_expand_kernel( const SvTask* __restrict__ tasks, int64_t ntas
 }
 
 template <bool BT>
-__global__ void __launch_bounds__( 288 ) gemm_solve_dmma_kernel( const SvGemm* __restrict__ tasks, const SvTile* __restrict__ tiles, const double* __restrict__ zeros ) {
-  constexpr int BM = 64, BN = 64, WM = 32, WN = 16, STAGES = 4, BK = 16;
+__global__ void __launch_bounds__( 288, 2 ) gemm_solve_dmma_kernel( const SvGemm* __restrict__ tasks, const SvTile* __restrict__ tiles, const double* __restrict__ zeros ) {
+  constexpr int BM = 64, BN = 64, WM = 32, WN = 16, BK = BT ? 32 : 16, STAGES = BT ? 3 : 4;      /* BT: 64 row-run copies per stage -- 256-byte runs keep the copy issue rate below the tensor pipe's appetite */
   constexpr int NCW = 8, LDA = BM + 4, LDB = BT ? BK + 4 : BN + 4;
   constexpr int BSTAGE = BT ? BN * LDB : BK * LDB;
   constexpr int MT = WM / 8, NTL = WN / 8;
@@ -1178,7 +1318,7 @@ __global__ void __launch_bounds__( 288 ) gemm_solve_dmma_kernel( const SvGemm* _
         const int slot = kt % STAGES, use = kt / STAGES;
         if ( lane == 0 ) { if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 ); mbar_expect_tx( &full[slot], BK * ra + nval * cb ); }
         __syncwarp();
-        if ( lane < 16 ) { const int kq = kt * BK + lane; bulk_g2s( As + slot * BK * LDA + lane * LDA, kq < K ? ( const void* )( Ag - sa + ( int64_t )kq * t.lda ) : ( const void* )zeros, ra, &full[slot] ); }
+        { const int kq = kt * BK + lane; bulk_g2s( As + slot * BK * LDA + lane * LDA, kq < K ? ( const void* )( Ag - sa + ( int64_t )kq * t.lda ) : ( const void* )zeros, ra, &full[slot] ); }      /* BK = 32: one k-column of A per lane */
 #pragma unroll
         for ( int h = 0; h < 2; h++ ) { const int nn = lane + 32 * h; if ( nn < nval ) bulk_g2s( Bs + slot * BSTAGE + nn * LDB, Bg + ( int64_t )nn * t.ldb + kt * BK - sbk, cb, &full[slot] ); }
       }

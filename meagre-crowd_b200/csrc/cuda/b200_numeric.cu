@@ -82,7 +82,7 @@ constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
 constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 constexpr int SVG_SMEM_NT = GEMM_STAGES * 16 * ( 68 + 68 ) * 8 + 2 * GEMM_STAGES * 8;                 /* gemm_solve_dmma_kernel<false> */
-constexpr int SVG_SMEM_BT = GEMM_STAGES * ( 16 * 68 + 64 * 20 ) * 8 + 2 * GEMM_STAGES * 8;            /* gemm_solve_dmma_kernel<true>  */
+constexpr int SVG_SMEM_BT = 3 * ( 32 * 68 + 64 * 36 ) * 8 + 2 * 3 * 8;                                /* gemm_solve_dmma_kernel<true>: BK = 32, 3 stages */
 
 enum LaunchKind { LK_MEMSET_CB = 0, LK_ASM, LK_DIAG, LK_TRSM, LK_GEMM_BIG, LK_TRSM_MMA, LK_NOP, LK_DIAG_S, LK_SMALL_FRONT, LK_XFER_CB, LK_BCAST, LK_GATHER, LK_COUNT };
 static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_block", "trsm_rows", "gemm_dmma", "trsm_dmma", "nop", "diag_block_small", "small_front", "nccl_cb_columns", "nccl_panel_bcast", "nccl_factor_gather" };
@@ -95,8 +95,8 @@ struct Launch { int kind; int64_t first; int64_t count; int depth; double flops;
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
-enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_TRI, SK_FWD_UPD, SK_BWD_GATHER, SK_BWD_UPD, SK_BWD_TRI, SK_COUNT };
-/* one launch of a sweep: gather / zero launches use first,count; product launches carry their tiles in the FMA list (t0,nt: 64 outputs per
+enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_TRI, SK_FWD_UPD, SK_BWD_GATHER, SK_BWD_UPD, SK_BWD_TRI, SK_FWD_SMALL, SK_BWD_SMALL, SK_COUNT };
+/* one launch of a sweep: gather / zero launches use first,count; product launches carry their tiles in the FMA list (t0,nt: 32 outputs per
  * tile for gemv-type tasks, 32 for gemvT-type) and in the tensor-path list (g0,ng: 64 outputs per tile) */
 struct SLaunch { int kind; int depth; int64_t first, count; int64_t t0, nt; int64_t g0, ng; };
 
@@ -142,7 +142,7 @@ struct b200_ctx {
   DevVec<AsmTask> asm_tasks;
   std::vector<Launch> launches;
   /* solve */
-  DevVec<SvTask> sv_tasks; DevVec<SvTile> sv_tiles_v, sv_tiles_t, sv_tiles_g; DevVec<GatherTask> bgather_tasks;
+  DevVec<SvTask> sv_tasks; DevVec<SvTile> sv_tiles_v, sv_tiles_t, sv_tiles_g; DevVec<GatherTask> bgather_tasks; DevVec<int> sv_small;
   SvGemm* dSvGemm = nullptr; int sv_gemm_p = 0; int solve_wide_min = SB_WIDE_MIN;
   std::vector<SLaunch> slaunches;
   int64_t sinvsize = 0;
@@ -161,7 +161,7 @@ struct b200_ctx {
   double prof_ms[LK_COUNT] = { 0 }; int64_t prof_n[LK_COUNT] = { 0 };
   double sprof_ms[SK_COUNT] = { 0 }; int64_t sprof_n[SK_COUNT] = { 0 };
   b200_stats_t stats;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evs = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evs = nullptr, evs2 = nullptr;
   std::vector<cudaEvent_t> lvl_ev; std::vector<float> lvl_ms;   /* update-stream time stamps at level boundaries (diagnostics) */
   int64_t device_bytes = 0;
 };
@@ -178,7 +178,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaGetDeviceProperties( &c->prop, device ) );
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
     CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); }
-  CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) );
+  CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) ); CKN( cudaEventCreateWithFlags( &c->evs2, cudaEventDisableTiming ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
@@ -192,6 +192,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
+  CKN( cudaFuncSetAttribute( sv_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_gemv_smem<4>() ) );
+  CKN( cudaFuncSetAttribute( sv_gemvT_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_gemvT_smem<4>() ) );
   CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_NT ) );
   CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_BT ) );
   { const char* e = getenv( "B200_SOLVE_WIDE_MIN" ); if ( e ) c->solve_wide_min = std::max( 2 * SB, atoi( e ) ); }     /* test hook: wide solve blocks on small problems */
@@ -254,7 +256,7 @@ static void release_symbolic( b200_ctx* c ) {
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
   c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
   c->gemm_tasks.release(); c->tiles_big.release(); c->tiles_small.release(); c->diag_tasks.release(); c->trsm_tasks.release(); c->trsm_tiles.release(); c->asm_tasks.release();
-  c->small_sns.release(); c->sv_tasks.release(); c->sv_tiles_v.release(); c->sv_tiles_t.release(); c->sv_tiles_g.release(); c->gather_tasks.release(); c->bgather_tasks.release();
+  c->small_sns.release(); c->sv_tasks.release(); c->sv_tiles_v.release(); c->sv_tiles_t.release(); c->sv_tiles_g.release(); c->gather_tasks.release(); c->bgather_tasks.release(); c->sv_small.release();
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dSvGemm );
   c->dR = c->dD = c->dZ = nullptr; c->dSvGemm = nullptr; c->sv_gemm_p = 0;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
@@ -269,7 +271,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   cudaStreamSynchronize( c->stream ); cudaStreamSynchronize( c->stream2 ); cudaStreamSynchronize( c->stream3 ); cudaStreamSynchronize( c->stream4 );   /* pending NCCL sends read dL / dInv */
   release_symbolic( c );
   cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dTiny ); cudaFree( c->dMaxBits ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
-  cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs );
+  cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs ); cudaEventDestroy( c->evs2 );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
   for ( cudaEvent_t e : c->lvl_ev ) cudaEventDestroy( e );
   if ( c->comm ) g_nccl.CommDestroy( c->comm );
@@ -725,7 +727,11 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   /* ---- solve schedule: forward deepest->root, backward root->deepest.  Per level and block step two launches: the triangular product
    * with the block's explicit inverse, then the update of everything the block feeds (kernels: sv_gemv / sv_gemvT, or the tensor path) */
   {
-    std::vector<SvTask> tk; std::vector<SvTile> tv, tt, tg; std::vector<GatherTask> gp, bg;
+    std::vector<SvTask> tk; std::vector<SvTile> tv, tt, tg; std::vector<GatherTask> gp, bg; std::vector<int> sm;
+    const bool use_small = getenv( "B200_NO_SMALL_SOLVE" ) == nullptr;
+    auto is_small = [&]( int s ) { return use_small && meta[s].k <= KC && meta[s].f <= 4 * SVS_THREADS; };      /* one canonical chunk, one solve block: the fused per-supernode kernels */
+    std::vector<std::vector<int>> big( S->maxdepth + 1 ); std::vector<std::pair<int64_t, int64_t>> small_rng( S->maxdepth + 1 );
+    for ( int d = 0; d <= S->maxdepth; d++ ) { small_rng[d].first = ( int64_t )sm.size(); for ( int s : levels[d] ) { if ( is_small( s ) ) sm.push_back( s ); else big[d].push_back( s ); } small_rng[d].second = ( int64_t )sm.size() - small_rng[d].first; }
     std::vector<SLaunch>& SS = c->slaunches;
     const double* Fb = c->dL;                       /* forward sweep: L */
     const double* Mb = LU ? c->dU : c->dL;          /* backward sweep: L' x, or U x through the U' panels */
@@ -734,7 +740,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     auto add_task = [&]( const SvTask& x, bool T ) {
       if ( x.N <= 0 || x.K <= 0 ) return;
       const int id = ( int )tk.size(); tk.push_back( x );
-      if ( T ) for ( int o = 0; o < x.N; o += GT_COLS ) tt.push_back( { id, o } ); else for ( int o = 0; o < x.N; o += KC ) tv.push_back( { id, o } );
+      if ( T ) for ( int o = 0; o < x.N; o += GT_COLS ) tt.push_back( { id, o } ); else for ( int o = 0; o < x.N; o += GV_ROWS ) tv.push_back( { id, o } );
       for ( int o = 0; o < x.N; o += 64 ) tg.push_back( { id, o } );
     };
     auto close = [&]( int kind, int d, const Mark& m0, bool T ) {
@@ -749,16 +755,18 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         for ( int s : lv ) { bool any = false; for ( int ci = meta[s].child_begin; ci < meta[s].child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
           if ( any ) for ( int lo = 0; lo < meta[s].f; lo += GATHER_ROWS ) gp.push_back( { s, lo, std::min( meta[s].f, lo + GATHER_ROWS ) } ); }
         if ( ( int64_t )gp.size() > g0 ) SS.push_back( { SK_FWD_GATHER, d, g0, ( int64_t )gp.size() - g0, 0, 0, 0, 0 } ); }
-      int nblk = 0; for ( int s : lv ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      if ( small_rng[d].second > 0 ) SS.push_back( { SK_FWD_SMALL, d, small_rng[d].first, small_rng[d].second, 0, 0, 0, 0 } );
+      const std::vector<int>& bl = big[d];
+      int nblk = 0; for ( int s : bl ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
       for ( int t = 0; t < nblk; t++ ) {
         Mark m0 = mark( false );
-        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
           const int nb = std::min( m.sbw, m.k - j0 );
           SvTask x; x.M = c->dSinvF + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 1; x.mode = 1;
           x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0 + j0; add_task( x, false ); }
         close( SK_FWD_TRI, d, m0, false );
         m0 = mark( false );
-        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
           const int nb = std::min( m.sbw, m.k - j0 );
           SvTask x; x.ld = m.ld; x.K = nb; x.tri = 0; x.mode = 0; x.vsel = 1; x.voff = m.c0 + j0;
           x.M = Fb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.N = m.k - j0 - nb; x.dsel = 0; x.doff = m.c0 + j0 + nb; add_task( x, false );      /* pivot rows below the block */
@@ -769,30 +777,32 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     for ( int d = 0; d <= S->maxdepth; d++ ) {
       const std::vector<int>& lv = levels[d];
       const int wsel = 2 + ( d & 1 );
+      if ( small_rng[d].second > 0 ) SS.push_back( { SK_BWD_SMALL, d, small_rng[d].first, small_rng[d].second, 0, 0, 0, 0 } );
+      const std::vector<int>& bl = big[d];
       { const int64_t g0 = ( int64_t )bg.size();
-        for ( int s : lv ) { const int u = meta[s].f - meta[s].k; for ( int lo = 0; lo < u; lo += GATHER_ROWS ) bg.push_back( { s, lo, std::min( u, lo + GATHER_ROWS ) } ); }
+        for ( int s : bl ) { const int u = meta[s].f - meta[s].k; for ( int lo = 0; lo < u; lo += GATHER_ROWS ) bg.push_back( { s, lo, std::min( u, lo + GATHER_ROWS ) } ); }
         if ( ( int64_t )bg.size() > g0 ) SS.push_back( { SK_BWD_GATHER, d, g0, ( int64_t )bg.size() - g0, 0, 0, 0, 0 } ); }
       { Mark m0 = mark( true );
-        for ( int s : lv ) { const SnMeta& m = meta[s];
+        for ( int s : bl ) { const SnMeta& m = meta[s];
           SvTask x; x.M = Mb + m.lptr + m.k; x.ld = m.ld; x.K = m.f - m.k; x.N = m.k; x.tri = 0; x.mode = 0; x.vsel = wsel; x.voff = m.wptr; x.dsel = 1; x.doff = m.c0; add_task( x, true ); }
         close( SK_BWD_UPD, d, m0, true ); }
-      int nblk = 0; for ( int s : lv ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      int nblk = 0; for ( int s : bl ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
       for ( int t = nblk - 1; t >= 0; t-- ) {
         Mark m0 = mark( false );
-        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
           const int nb = std::min( m.sbw, m.k - j0 );
           SvTask x; x.M = c->dSinvB + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 2; x.mode = 1;
           x.vsel = 1; x.voff = m.c0 + j0; x.dsel = 0; x.doff = m.c0 + j0; add_task( x, false ); }
         close( SK_BWD_TRI, d, m0, false );
         if ( t == 0 ) break;
         m0 = mark( true );
-        for ( int s : lv ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
           const int nb = std::min( m.sbw, m.k - j0 );
           SvTask x; x.M = Mb + m.lptr + j0; x.ld = m.ld; x.K = nb; x.N = j0; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0; add_task( x, true ); }
         close( SK_BWD_UPD, d, m0, true );
       }
     }
-    if ( c->sv_tasks.upload( tk ) || c->sv_tiles_v.upload( tv ) || c->sv_tiles_t.upload( tt ) || c->sv_tiles_g.upload( tg ) || c->gather_tasks.upload( gp ) || c->bgather_tasks.upload( bg ) ) return B200_ERR_CUDA;
+    if ( c->sv_tasks.upload( tk ) || c->sv_tiles_v.upload( tv ) || c->sv_tiles_t.upload( tt ) || c->sv_tiles_g.upload( tg ) || c->gather_tasks.upload( gp ) || c->bgather_tasks.upload( bg ) || c->sv_small.upload( sm ) ) return B200_ERR_CUDA;
     if ( !c->dry && tk.size() ) CK( cudaMalloc( &c->dSvGemm, tk.size() * sizeof( SvGemm ) ) );
     c->sv_gemm_p = 0;
   }
@@ -948,24 +958,49 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
   permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, pitch, c->dY );
   nl += 2;
   const unsigned gy = ( unsigned )( ( p + 63 ) / 64 );
+  int tqs = 0; while ( tqs < 5 && ( 1 << tqs ) < pitch ) tqs++;      /* gather kernels: 2^tqs threads along the right-hand sides of a row */
+  /* the fused small-supernode kernel of a level is independent of the level's generic launches: it runs on a second stream,
+   * forked after the level's gather and joined before the next level (or the turn of the sweep) begins */
+  cudaStream_t st2 = c->profile ? st : c->stream2;
+  bool forked = false; int cur_depth = -1, cur_dir = 0;
   for ( const SLaunch& l : c->slaunches ) {
     const int a = l.depth & 1, ac = ( l.depth + 1 ) & 1;
+    const int dir = ( l.kind == SK_BWD_GATHER || l.kind == SK_BWD_UPD || l.kind == SK_BWD_TRI || l.kind == SK_BWD_SMALL ) ? 1 : 0;
+    if ( ( l.depth != cur_depth || dir != cur_dir ) && forked ) { CK( cudaEventRecord( c->evs, st2 ) ); CK( cudaStreamWaitEvent( st, c->evs, 0 ) ); forked = false; }
+    cur_depth = l.depth; cur_dir = dir;
     if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
+    cudaStream_t sst = st;
+    if ( ( l.kind == SK_FWD_SMALL || l.kind == SK_BWD_SMALL ) && st2 != st ) { CK( cudaEventRecord( c->evs2, st ) ); CK( cudaStreamWaitEvent( st2, c->evs2, 0 ) ); forked = true; sst = st2; }
     switch ( l.kind ) {
       case SK_FWD_ZERO_W: CK( cudaMemsetAsync( c->dW[a], 0, ( size_t )l.count * pitch * 8, st ) ); break;
-      case SK_FWD_GATHER: fwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->gather_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, pitch, c->dW[a], c->dW[ac] ); break;
-      case SK_BWD_GATHER: bwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->bgather_tasks.d + l.first, c->sn.d, c->rowidx.d, c->dY, pitch, c->dW[a] ); break;
+      case SK_FWD_GATHER: fwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->gather_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dY, pitch, tqs, c->dW[a], c->dW[ac] ); break;
+      case SK_BWD_GATHER: bwd_gather_kernel<<<( unsigned )l.count, 256, 0, st>>>( c->bgather_tasks.d + l.first, c->sn.d, c->rowidx.d, c->dY, pitch, tqs, c->dW[a] ); break;
+      case SK_FWD_SMALL: {
+        const int pch = tensor ? ( p + 7 ) / 8 : 1; const unsigned g = ( unsigned )( l.count * pch ); const int* sl = c->sv_small.d + l.first;
+        if ( tensor ) sv_small_fwd_kernel<8><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, c->dW[a], p, pitch );
+        else if ( pct == 1 ) sv_small_fwd_kernel<1><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, c->dW[a], p, pitch );
+        else if ( pct == 2 ) sv_small_fwd_kernel<2><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, c->dW[a], p, pitch );
+        else sv_small_fwd_kernel<4><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, c->dL, c->dSinvF, c->dY, c->dZ, c->dW[a], p, pitch );
+        break; }
+      case SK_BWD_SMALL: {
+        const int pch = tensor ? ( p + 7 ) / 8 : 1; const unsigned g = ( unsigned )( l.count * pch ); const int* sl = c->sv_small.d + l.first;
+        const double* Mb = c->kind == B200_KIND_CHOLESKY ? c->dL : c->dU;
+        if ( tensor ) sv_small_bwd_kernel<8><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dY, c->dZ, p, pitch );
+        else if ( pct == 1 ) sv_small_bwd_kernel<1><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dY, c->dZ, p, pitch );
+        else if ( pct == 2 ) sv_small_bwd_kernel<2><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dY, c->dZ, p, pitch );
+        else sv_small_bwd_kernel<4><<<g, SVS_THREADS, 0, sst>>>( sl, pch, c->sn.d, Mb, c->dSinvB, c->rowidx.d, c->dY, c->dZ, p, pitch );
+        break; }
       case SK_FWD_TRI: case SK_FWD_UPD: case SK_BWD_TRI:
         if ( tensor ) gemm_solve_dmma_kernel<false><<<dim3( ( unsigned )l.ng, gy ), 288, SVG_SMEM_NT, st>>>( c->dSvGemm, c->sv_tiles_g.d + l.g0, c->dZeros );
-        else if ( pct == 1 ) sv_gemv_kernel<1><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
-        else if ( pct == 2 ) sv_gemv_kernel<2><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
-        else sv_gemv_kernel<4><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
+        else if ( pct == 1 ) sv_gemv_kernel<1><<<( unsigned )l.nt, 256, sv_gemv_smem<1>(), st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
+        else if ( pct == 2 ) sv_gemv_kernel<2><<<( unsigned )l.nt, 256, sv_gemv_smem<2>(), st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
+        else sv_gemv_kernel<4><<<( unsigned )l.nt, 256, sv_gemv_smem<4>(), st>>>( c->sv_tasks.d, c->sv_tiles_v.d + l.t0, B, p, pitch );
         break;
       case SK_BWD_UPD:
         if ( tensor ) gemm_solve_dmma_kernel<true><<<dim3( ( unsigned )l.ng, gy ), 288, SVG_SMEM_BT, st>>>( c->dSvGemm, c->sv_tiles_g.d + l.g0, c->dZeros );
-        else if ( pct == 1 ) sv_gemvT_kernel<1><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
-        else if ( pct == 2 ) sv_gemvT_kernel<2><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
-        else sv_gemvT_kernel<4><<<( unsigned )l.nt, 256, 0, st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
+        else if ( pct == 1 ) sv_gemvT_kernel<1><<<( unsigned )l.nt, 128, sv_gemvT_smem<1>(), st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
+        else if ( pct == 2 ) sv_gemvT_kernel<2><<<( unsigned )l.nt, 128, sv_gemvT_smem<2>(), st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
+        else sv_gemvT_kernel<4><<<( unsigned )l.nt, 128, sv_gemvT_smem<4>(), st>>>( c->sv_tasks.d, c->sv_tiles_t.d + l.t0, B, p, pitch );
         break;
     }
     nl++;
@@ -976,6 +1011,7 @@ static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64
       if ( trace_all ) fprintf( stderr, "slaunch kind=%d depth=%d tiles=%lld gtiles=%lld ms=%.4f\n", l.kind, l.depth, ( long long )l.nt, ( long long )l.ng, ms );
     }
   }
+  if ( forked ) { CK( cudaEventRecord( c->evs, st2 ) ); CK( cudaStreamWaitEvent( st, c->evs, 0 ) ); }
   permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dY, c->perm.d, n, p, pitch, d_x );
   return B200_OK;
 }
@@ -1080,7 +1116,7 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   std::string s;
   char line[256];
   for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
-  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_tri", "solve_fwd_upd", "solve_bwd_gather", "solve_bwd_upd", "solve_bwd_tri" };
+  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_tri", "solve_fwd_upd", "solve_bwd_gather", "solve_bwd_upd", "solve_bwd_tri", "solve_fwd_small", "solve_bwd_small" };
   for ( int k = 0; k < SK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", sname[k], ( long long )c->sprof_n[k], c->sprof_ms[k] ); s += line; }
   { float t0 = 0; if ( !c->lvl_ev.empty() ) cudaEventElapsedTime( &t0, c->ev0, c->lvl_ev[0] ); snprintf( line, sizeof( line ), "levels_ms(deepest first; prologue %.2f):", t0 ); s += line;
     for ( float v : c->lvl_ms ) { snprintf( line, sizeof( line ), " %.2f", v ); s += line; } s += "\n"; }
