@@ -50,6 +50,8 @@ struct TrsmTask {
   double* B; int ldb; int m;     /* m rows starting at B, nb columns */
   const double* T; int nb;       /* X = B * T'   (T nb x nb, ld nb)  */
   const int* piv;                /* LU U-panel: permute the nb columns of B on load (NULL = none) */
+  double* out;                   /* result rows (same ld); NULL = in place */
+  int full;                      /* 1: T is a full matrix (LDL': interchanges folded in), 0: lower triangular */
 };
 struct RowTile { int task; int r0; };
 
@@ -462,6 +464,126 @@ __global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __re
   }
 }
 
+/* ------------------------------------------------------ diagonal block: LDL'
+ * Symmetric indefinite nb x nb block (nb <= 64, lower triangle in the L panel):  P A P' = L D L'  with Bunch-Kaufman partial
+ * pivoting (1x1 and 2x2 pivots, alpha = (1+sqrt(17))/8), the interchanges restricted to the block's own rows -- the same rule the
+ * LU path follows; a column whose candidates are all below `tiny` is statically perturbed and counted.
+ * Outputs (the conventions of the LU path, so that the row update, the solve-block inverses and the sweeps are shared):
+ *   inv  = T  = inv(L) P        -> rows below:  W21 = A21 T'   (W = L D, kept in the second panel; it plays the part of U')
+ *   inv2 = T2 = inv(D) inv(L) P -> rows below:  L21 = A21 T2'
+ * Both are full nb x nb matrices (the interchanges are folded in as a column permutation).  The panels' diagonal blocks receive
+ * L (unit lower, pivot order) and D (block diagonal, lower part); nothing reads them again. */
+constexpr int LDLT_SMEM = ( 3 * NB * ( NB + 1 ) + 2 * NB ) * 8 + 3 * NB * 4;
+__global__ void __launch_bounds__( 256 ) ldlt_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed ) {
+  extern __shared__ double dsm[];
+  double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );                          /* full symmetric active matrix; columns < j hold L */
+  double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );          /* inv(L)                                         */
+  double ( *y )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + 2 * NB * ( NB + 1 ) );      /* inv(D) inv(L)                                  */
+  double* c1 = dsm + 3 * NB * ( NB + 1 );       /* column j   of the active matrix before elimination */
+  double* c2 = c1 + NB;                         /* column j+1 (2x2 pivots)                            */
+  int* sig = reinterpret_cast<int*>( c2 + NB ); /* position -> original row of the block              */
+  int* two = sig + NB;                          /* two[j] = 1: (j, j+1) is a 2x2 pivot                */
+  __shared__ int s_kp, s_step; __shared__ double s_d11, s_d21, s_d22;
+  const DiagTask t = tasks[blockIdx.x];
+  const int nb = t.nb, tid = threadIdx.x, lane = tid & 31;
+  const double tiny = *tiny_p;
+  const double alpha = 0.6403882032022076;
+  for ( int e = tid; e < nb * nb; e += 256 ) { const int r = e % nb, c = e / nb; const double v = r >= c ? t.A[r + ( int64_t )c * t.lda] : t.A[c + ( int64_t )r * t.lda]; a[r][c] = v; x[r][c] = 0.0; y[r][c] = 0.0; }
+  if ( tid < NB ) { sig[tid] = tid; two[tid] = 0; }
+  __syncthreads();
+  int j = 0;
+  while ( j < nb ) {
+    if ( tid < 32 ) {   /* ---- pivot choice (warp 0) */
+      double colmax = 0.0; int imax = j;
+      for ( int i = j + 1 + lane; i < nb; i += 32 ) { const double v = fabs( a[i][j] ); if ( v > colmax ) { colmax = v; imax = i; } }
+      for ( int o = 16; o; o >>= 1 ) { const double ov = __shfl_xor_sync( 0xffffffffu, colmax, o ); const int oi = __shfl_xor_sync( 0xffffffffu, imax, o ); if ( ov > colmax || ( ov == colmax && ov > 0.0 && oi < imax ) ) { colmax = ov; imax = oi; } }
+      const double absakk = fabs( a[j][j] );
+      int kp = j, step = 1;
+      if ( !( fmax( absakk, colmax ) > tiny ) ) {                  /* nothing usable in this column: static perturbation (also catches NaN) */
+        if ( lane == 0 ) { a[j][j] = ( a[j][j] < 0.0 ) ? -tiny : tiny; atomicAdd( nperturbed, 1 ); }
+      } else if ( absakk < alpha * colmax ) {
+        double rowmax = 0.0;
+        for ( int q = j + lane; q < nb; q += 32 ) if ( q != imax ) rowmax = fmax( rowmax, fabs( a[imax][q] ) );
+        for ( int o = 16; o; o >>= 1 ) rowmax = fmax( rowmax, __shfl_xor_sync( 0xffffffffu, rowmax, o ) );
+        if ( absakk * rowmax >= alpha * colmax * colmax ) { kp = j; }
+        else if ( fabs( a[imax][imax] ) >= alpha * rowmax ) { kp = imax; }
+        else { kp = imax; step = 2; }
+      }
+      if ( lane == 0 ) { s_kp = kp; s_step = step; }
+    }
+    __syncthreads();
+    const int step = s_step, kk = j + step - 1, kp = s_kp;
+    if ( kp != kk ) {   /* ---- symmetric interchange kk <-> kp: rows over all columns, then columns over all rows */
+      if ( tid < nb ) { const double tmp = a[kk][tid]; a[kk][tid] = a[kp][tid]; a[kp][tid] = tmp; }
+      __syncthreads();
+      if ( tid < nb && tid >= j ) { const double tmp = a[tid][kk]; a[tid][kk] = a[tid][kp]; a[tid][kp] = tmp; }      /* columns of the L part (< j) belong to other pivots: rows only */
+      if ( tid == 0 ) { const int s = sig[kk]; sig[kk] = sig[kp]; sig[kp] = s; }
+      __syncthreads();
+    }
+    if ( step == 1 ) {
+      if ( tid == 0 ) s_d11 = a[j][j];
+      if ( tid < nb ) c1[tid] = tid > j ? a[tid][j] : 0.0;
+      __syncthreads();
+      const double d = s_d11, rd = 1.0 / d;
+      for ( int e = tid; e < ( nb - j - 1 ) * ( nb - j - 1 ); e += 256 ) {
+        const int r = j + 1 + e % ( nb - j - 1 ), c = j + 1 + e / ( nb - j - 1 );
+        a[r][c] -= c1[r] * rd * c1[c];
+      }
+      if ( tid < nb && tid > j ) a[tid][j] = c1[tid] * rd;
+      __syncthreads();
+      j += 1;
+    } else {
+      if ( tid == 0 ) { s_d11 = a[j][j]; s_d21 = a[j + 1][j]; s_d22 = a[j + 1][j + 1]; two[j] = 1; }
+      if ( tid < nb ) { c1[tid] = tid > j + 1 ? a[tid][j] : 0.0; c2[tid] = tid > j + 1 ? a[tid][j + 1] : 0.0; }
+      __syncthreads();
+      /* inverse of the 2x2 pivot, scaled as in LAPACK dsytf2 for accuracy */
+      const double d21 = s_d21, e11 = s_d11 / d21, e22 = s_d22 / d21, tt = 1.0 / ( e11 * e22 - 1.0 ), sc = tt / d21;
+      for ( int e = tid; e < ( nb - j - 2 ) * ( nb - j - 2 ); e += 256 ) {
+        const int r = j + 2 + e % ( nb - j - 2 ), c = j + 2 + e / ( nb - j - 2 );
+        const double l1 = sc * ( e22 * c1[r] - c2[r] ), l2 = sc * ( e11 * c2[r] - c1[r] );      /* row r of L, columns j and j+1 */
+        a[r][c] -= l1 * c1[c] + l2 * c2[c];
+      }
+      if ( tid < nb && tid > j + 1 ) { a[tid][j] = sc * ( e22 * c1[tid] - c2[tid] ); a[tid][j + 1] = sc * ( e11 * c2[tid] - c1[tid] ); }
+      __syncthreads();
+      j += 2;
+    }
+  }
+  /* x = inverse of the unit lower L (a 2x2 pivot has l(j+1,j) = 0: its entry a[j+1][j] holds d21) */
+  {
+    const int col = tid >> 2, part = tid & 3;
+    if ( col < nb && part == 0 ) x[col][col] = 1.0;
+    __syncwarp();
+    for ( int i = 1; i < nb; i++ ) {
+      double s = 0.0;
+      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) { const double l = ( q + 1 == i && two[q] ) ? 0.0 : a[i][q]; s += l * x[q][col]; }
+      s += __shfl_xor_sync( 0xffffffffu, s, 1 ); s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+      if ( col < nb && i > col && part == 0 ) x[i][col] = -s;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  /* y = inv(D) x, row by row (2x2 pivots couple two rows) */
+  for ( int e = tid; e < nb * nb; e += 256 ) {
+    const int r = e % nb, c = e / nb;
+    double v;
+    if ( two[r] ) { const double d21 = a[r + 1][r], e11 = a[r][r] / d21, e22 = a[r + 1][r + 1] / d21, sc = 1.0 / ( ( e11 * e22 - 1.0 ) * d21 ); v = sc * ( e22 * x[r][c] - x[r + 1][c] ); }
+    else if ( r > 0 && two[r - 1] ) { const double d21 = a[r][r - 1], e11 = a[r - 1][r - 1] / d21, e22 = a[r][r] / d21, sc = 1.0 / ( ( e11 * e22 - 1.0 ) * d21 ); v = sc * ( e11 * x[r][c] - x[r - 1][c] ); }
+    else v = x[r][c] / a[r][r];
+    y[r][c] = v;
+  }
+  __syncthreads();
+  for ( int e = tid; e < nb * nb; e += 256 ) {
+    const int r = e % nb, c = e / nb;
+    t.inv[r + sig[c] * nb] = x[r][c];       /* T  = inv(L) P : column c of inv(L) lands in column sig[c] */
+    t.inv2[r + sig[c] * nb] = y[r][c];      /* T2 = inv(D) inv(L) P */
+    if ( r >= c ) {
+      const bool sub2 = r == c + 1 && two[c];
+      t.A[r + ( int64_t )c * t.lda] = r == c ? 1.0 : ( sub2 ? 0.0 : a[r][c] );
+      t.AU[r + ( int64_t )c * t.lda] = r == c ? a[r][r] : ( sub2 ? a[r][c] : 0.0 );
+    }
+  }
+}
+
 /* -------------------------------------------------------------- trsm rows
  * X = B * T' for a tile of 128 rows; T (nb x nb) is lower triangular, so column
  * c of X needs q <= c only.  B is overwritten.  4x8 register tile per thread. */
@@ -475,6 +597,7 @@ __global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __res
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows = min( 128, t.m - rt.r0 );
   double* Bg = t.B + rt.r0;
+  double* Og = ( t.out ? t.out : t.B ) + rt.r0;
   for ( int e = tid; e < NB * NB; e += 256 ) { int c = e % NB, q = e / NB; Ts[q * NB + c] = ( c < nb && q < nb ) ? t.T[c + q * nb] : 0.0; }
   for ( int e = tid; e < nb * 128; e += 256 ) {
     int r = e & 127, q = e >> 7;
@@ -495,7 +618,7 @@ __global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __res
     for ( int j = 0; j < 8; j++ ) acc[i][j] = 0.0;
   const int c0 = warp * 8;
   if ( c0 < nb ) {
-    const int qend = min( nb, c0 + 8 );
+    const int qend = t.full ? nb : min( nb, c0 + 8 );
     for ( int q = 0; q < qend; q++ ) {
       double bv[4], tv[8];
 #pragma unroll
@@ -512,7 +635,7 @@ __global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __res
       const int c = c0 + j;
       if ( c < nb ) {
 #pragma unroll
-        for ( int i = 0; i < 4; i++ ) { const int r = lane + 32 * i; if ( r < rows ) Bg[r + ( int64_t )c * t.ldb] = acc[i][j]; }
+        for ( int i = 0; i < 4; i++ ) { const int r = lane + 32 * i; if ( r < rows ) Og[r + ( int64_t )c * t.ldb] = acc[i][j]; }
       }
     }
   }

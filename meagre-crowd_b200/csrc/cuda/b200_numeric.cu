@@ -187,6 +187,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
   c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
+  CKN( cudaFuncSetAttribute( ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LDLT_SMEM ) );
   CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
   CKN( cudaFuncSetAttribute( small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM ) );
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
@@ -311,6 +312,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   release_symbolic( c );
   const int ns = S->ns, n = S->n;
   const bool LU = S->kind == B200_KIND_LU;
+  const bool LD = S->kind == B200_KIND_LDLT;      /* L D L': Cholesky's structure and updates, but a second panel W = L D in the place of U' and pivoting diagonal blocks */
+  const bool TWO = LU || LD;                       /* two panels per supernode */
   c->n = n; c->ns = ns; c->kind = S->kind; c->maxdepth = S->maxdepth; c->nnzA = S->nnzA;
   c->lsize = S->stored_nnzL; c->cb_arena[0] = S->cb_arena[0]; c->cb_arena[1] = S->cb_arena[1];
   c->flops_exact = S->flops * ( LU ? 2.0 : 1.0 ); c->flops_stored = S->stored_flops * ( LU ? 2.0 : 1.0 );
@@ -341,7 +344,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   }
   c->invsize = invoff; c->sinvsize = sinvoff;
   if ( c->world > 1 ) {
-    if ( LU ) { set_err( "multi-GPU factorization is built for Cholesky only (LU: run on one GPU)%s", "" ); return B200_ERR_ARG; }
+    if ( TWO ) { set_err( "multi-GPU factorization is built for Cholesky only (LU / LDL': run on one GPU)%s", "" ); return B200_ERR_ARG; }
     const char* md = getenv( "B200_MIN_DIST_FRONT" );
     c->plan = b200_plan_create( S, c->world, md ? atoi( md ) : 2048 );
     if ( !c->plan ) return B200_ERR_NOMEM;
@@ -355,22 +358,22 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     c->dL = reinterpret_cast<double*>( ( uintptr_t )1 << 40 ); c->dCB[0] = reinterpret_cast<double*>( ( uintptr_t )2 << 40 ); c->dCB[1] = reinterpret_cast<double*>( ( uintptr_t )3 << 40 );
     c->dInv = reinterpret_cast<double*>( ( uintptr_t )4 << 40 ); c->dSinvF = reinterpret_cast<double*>( ( uintptr_t )5 << 40 ); c->dSinvB = reinterpret_cast<double*>( ( uintptr_t )6 << 40 );
     c->dVals = reinterpret_cast<double*>( ( uintptr_t )7 << 40 );
-    if ( LU ) { c->dU = reinterpret_cast<double*>( ( uintptr_t )8 << 40 ); c->dInv2 = reinterpret_cast<double*>( ( uintptr_t )9 << 40 ); c->dSinvTmp = reinterpret_cast<double*>( ( uintptr_t )10 << 40 ); c->dPiv = reinterpret_cast<int*>( ( uintptr_t )11 << 40 ); }
+    if ( TWO ) { c->dU = reinterpret_cast<double*>( ( uintptr_t )8 << 40 ); c->dInv2 = reinterpret_cast<double*>( ( uintptr_t )9 << 40 ); c->dSinvTmp = reinterpret_cast<double*>( ( uintptr_t )10 << 40 ); c->dPiv = reinterpret_cast<int*>( ( uintptr_t )11 << 40 ); }
   }
-  const double need = ( double )c->lsize * 8.0 * ( LU ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( LU ? 3 : 2 ) + ( double )S->nnzA * 16.0;
+  const double need = ( double )c->lsize * 8.0 * ( TWO ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( TWO ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( TWO ? 3 : 2 ) + ( double )S->nnzA * 16.0;
   if ( !c->dry ) {
   size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
   if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
   CK( cudaMalloc( &c->dL, ( std::max<int64_t>( c->lsize, 1 ) + 32 ) * 8 ) );     /* + slack: the row-run copies of the backward tensor-path sweep read up to 17 rows past a slab */
   CK( cudaMemset( c->dL + std::max<int64_t>( c->lsize, 1 ), 0, 32 * 8 ) );
-  if ( LU ) { CK( cudaMalloc( &c->dU, ( std::max<int64_t>( c->lsize, 1 ) + 32 ) * 8 ) ); CK( cudaMemset( c->dU + std::max<int64_t>( c->lsize, 1 ), 0, 32 * 8 ) ); }
+  if ( TWO ) { CK( cudaMalloc( &c->dU, ( std::max<int64_t>( c->lsize, 1 ) + 32 ) * 8 ) ); CK( cudaMemset( c->dU + std::max<int64_t>( c->lsize, 1 ), 0, 32 * 8 ) ); }
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dCB[a], std::max<int64_t>( c->cb_arena[a], 2 ) * 8 ) );
   CK( cudaMalloc( &c->dInv, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) );     /* + slack: the bulk copies of an odd-aligned block read one double past it */
-  if ( LU ) { CK( cudaMalloc( &c->dInv2, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
+  if ( TWO ) { CK( cudaMalloc( &c->dInv2, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
   CK( cudaMalloc( &c->dSinvF, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );
   CK( cudaMemset( c->dSinvF, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvB, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );     /* padding rows of odd blocks stay zero */
-  if ( LU ) { CK( cudaMalloc( &c->dSinvTmp, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvTmp, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); }
+  if ( TWO ) { CK( cudaMalloc( &c->dSinvTmp, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvTmp, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); }
   }
   c->device_bytes = ( int64_t )need;
   { std::vector<int64_t> v( S->amap, S->amap + S->nnzA ); if ( c->amap.upload( v ) ) return B200_ERR_CUDA; }
@@ -456,7 +459,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
       }
       if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
     }
-    if ( c->use_small_front && !LU ) { /* small fronts: one CTA each, a single launch for the level (small_front_kernel) */
+    if ( c->use_small_front && !TWO ) { /* small fronts: one CTA each, a single launch for the level (small_front_kernel) */
       const int64_t s0 = ( int64_t )smalls.size();
       std::vector<int> rest;
       for ( int s : lv ) { if ( meta[s].k <= SF_KMAX && meta[s].f <= SF_FMAX && !is_dist( s ) ) smalls.push_back( s ); else rest.push_back( s ); }
@@ -487,9 +490,10 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
             const SnMeta& m = meta[s];
             if ( j0 >= m.k || !owns( s, J ) ) continue;
             const int nb = std::min( NB, m.k - j0 ); const int kk = j0 - J;
-            double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+            double* Lp = Lb + m.lptr; double* Up = TWO ? Ub + m.lptr : nullptr;
             double fl = 0;
-            if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );
+            if ( LD ) add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Up + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );      /* A -= L (L D)' */
+            else if ( !LU ) add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );
             else {
               add_gemm( gt, tb, ts, fl, Lp + j0 + ( int64_t )j0 * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, Up + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, 0 );
               add_gemm( gt, tb, ts, fl, Up + j0 + ( int64_t )j0 * m.ld, m.ld, Up + j0 + ( int64_t )J * m.ld, m.ld, Lp + j0 + ( int64_t )J * m.ld, m.ld, m.f - j0, nb, kk, 1, -1 );
@@ -504,11 +508,11 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
             const SnMeta& m = meta[s];
             if ( j0 >= m.k || !owns( s, J ) ) continue;
             const int nb = std::min( NB, m.k - j0 );
-            if ( !LU && ( pass == 0 ) != ( nb == NB ) ) continue;
-            if ( LU && pass == 1 ) continue;
+            if ( !TWO && ( pass == 0 ) != ( nb == NB ) ) continue;
+            if ( TWO && pass == 1 ) continue;
             DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
-            x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = LU ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
-            x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+            x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = TWO ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
+            x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = TWO ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
             x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
             dt.push_back( x );
           }
@@ -519,7 +523,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( d1 > d0 ) LS.push_back( { LK_DIAG, d0, d1 - d0, d, 0.0 } );
         if ( ( int64_t )dt.size() > d1 ) LS.push_back( { LK_DIAG_S, d1, ( int64_t )dt.size() - d1, d, 0.0 } );
         /* rows below the diagonal block */
-        const int64_t tl0 = ( int64_t )ttl.size(); std::vector<Tile> tbt;
+        const int64_t tl0 = ( int64_t )ttl.size(); std::vector<Tile> tbt, tbt2; std::vector<RowTile> ttl2;
         double tflops = 0;
         for ( int s : lv ) {
           const SnMeta& m = meta[s];
@@ -527,21 +531,41 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           const int nb = std::min( NB, m.k - j0 ); const int below = m.f - j0 - nb;
           if ( below <= 0 ) continue;
           const double* inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB;
-          const double* inv2 = LU ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+          const double* inv2 = TWO ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
+          double* Bp = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld;
+          double* Wp = TWO ? Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld : nullptr;
+          if ( LD ) { /* W21 = A21 T' into the second panel first, then L21 = A21 T2' in place (two launches: the second overwrites what the first reads) */
+            if ( nb == NB && c->use_bulk ) {
+              double dummy = 0; size_t ntask = gt.size();
+              add_gemm( gt, tbt, ts, dummy, Wp, m.ld, Bp, m.ld, inv, nb, below, nb, nb, 0, 0 );
+              if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
+              ntask = gt.size();
+              add_gemm( gt, tbt2, ts, dummy, Bp, m.ld, Bp, m.ld, inv2, nb, below, nb, nb, 0, 0 );
+              if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
+            } else {
+              TrsmTask x; x.B = Bp; x.ldb = m.ld; x.m = below; x.nb = nb; x.T = inv; x.piv = nullptr; x.out = Wp; x.full = 1;
+              int id = ( int )tt.size(); tt.push_back( x );
+              for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
+              TrsmTask y = x; y.T = inv2; y.out = nullptr;
+              id = ( int )tt.size(); tt.push_back( y );
+              for ( int r0 = 0; r0 < below; r0 += 128 ) ttl2.push_back( { id, r0 } );
+            }
+            tflops += 2.0 * below * nb * nb;
+            continue;
+          }
           if ( nb == NB && c->use_bulk ) {   /* X = B T' on the tensor pipe: C = A B' with C = A = the rows below, B = the inverse diagonal block (in place: one CTA owns whole rows) */
             double dummy = 0; const size_t ntask = gt.size();
-            double* Bp = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld;
             add_gemm( gt, tbt, ts, dummy, Bp, m.ld, Bp, m.ld, LU ? inv2 : inv, nb, below, nb, nb, 0, 0 );
             if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
             tflops += ( double )below * nb * nb;
           } else {
-          TrsmTask x; x.B = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.ldb = m.ld; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr;
+          TrsmTask x; x.B = Bp; x.ldb = m.ld; x.m = below; x.nb = nb; x.T = LU ? inv2 : inv; x.piv = nullptr; x.out = nullptr; x.full = 0;
           int id = ( int )tt.size(); tt.push_back( x );
           for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
           tflops += ( double )below * nb * nb;
           }
           if ( LU ) {
-            TrsmTask y; y.B = Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0;
+            TrsmTask y; y.B = Wp; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0; y.out = nullptr; y.full = 0;
             const int id = ( int )tt.size(); tt.push_back( y );
             for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
             tflops += ( double )below * nb * nb;
@@ -549,6 +573,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         }
         if ( ( int64_t )ttl.size() > tl0 ) LS.push_back( { LK_TRSM, tl0, ( int64_t )ttl.size() - tl0, d, tflops } );
         if ( !tbt.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt.size(), d, tflops } ); tb.insert( tb.end(), tbt.begin(), tbt.end() ); }
+        if ( !ttl2.empty() ) { LS.push_back( { LK_TRSM, ( int64_t )ttl.size(), ( int64_t )ttl2.size(), d, 0.0 } ); ttl.insert( ttl.end(), ttl2.begin(), ttl2.end() ); }
+        if ( !tbt2.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt2.size(), d, 0.0 } ); tb.insert( tb.end(), tbt2.begin(), tbt2.end() ); }
         if ( any_dist ) { /* the 64 columns just finished go straight to the owner of the NEXT panel, while the rest of this panel is
                            * still being factored: only the last block's transfer stays on the critical path */
           const int64_t m0 = ( int64_t )MS.size(); bool i_recv = false, i_send = false;
@@ -622,7 +648,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           if ( J >= m.k ) continue;
           const int kb = std::min( NBO, m.k - J ); const int Jn = J + kb; const int u = m.f - m.k;
           const int Jn2 = std::min( m.k, Jn + NBO );           /* end of the next outer panel */
-          double* Lp = Lb + m.lptr; double* Up = LU ? Ub + m.lptr : nullptr;
+          double* Lp = Lb + m.lptr; double* Up = TWO ? Ub + m.lptr : nullptr;
           double* cb = CB + m.cbptr;
           if ( is_dist( s ) ) { /* my column blocks only (Cholesky) */
             const int ldu = ( u + 1 ) & ~1;
@@ -644,7 +670,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           const int c_lo = part == 0 ? Jn : Jn2, c_hi = part == 0 ? Jn2 : m.k;   /* pivot columns updated by this part */
           if ( c_lo < c_hi ) {
             double* Cl = Lp + c_lo + ( int64_t )c_lo * m.ld; const double* Al = Lp + c_lo + ( int64_t )J * m.ld;
-            if ( !LU ) add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Al, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
+            if ( LD ) add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Up + c_lo + ( int64_t )J * m.ld, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
+            else if ( !LU ) add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Al, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
             else {
               double* Cu = Up + c_lo + ( int64_t )c_lo * m.ld; const double* Au = Up + c_lo + ( int64_t )J * m.ld;
               add_gemm( gt, tb, ts, fl, Cl, m.ld, Al, m.ld, Au, m.ld, m.f - c_lo, c_hi - c_lo, kb, 1, 0 );
@@ -653,7 +680,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           }
           if ( part == 1 && u > 0 ) {
             const double* Al = Lp + m.k + ( int64_t )J * m.ld;
-            if ( !LU ) add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Al, m.ld, u, u, kb, 1, 0 );
+            if ( LD ) add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Up + m.k + ( int64_t )J * m.ld, m.ld, u, u, kb, 1, 0 );
+            else if ( !LU ) add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Al, m.ld, u, u, kb, 1, 0 );
             else add_gemm( gt, tb, ts, fl, cb, ( u + 1 ) & ~1, Al, m.ld, Up + m.k + ( int64_t )J * m.ld, m.ld, u, u, kb, 0, 0 );
           }
         }
@@ -716,9 +744,9 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         const int64_t off = m.sinv + ( int64_t )( j0 / m.sbw ) * m.sbw * m.sbw;
         for ( int jb = 0; jb * NB < nb; jb++ ) {
           SinvTask x; x.P = Lb + m.lptr; x.ld = m.ld; x.j0 = j0; x.nb = nb; x.jb = jb; x.inv64 = c->dInv + m.invptr; x.ldx = ( nb + 1 ) & ~1;
-          x.piv = LU ? c->dPiv + m.c0 : nullptr; x.X = c->dSinvF + off; x.XT = LU ? nullptr : c->dSinvB + off;
+          x.piv = LU ? c->dPiv + m.c0 : nullptr; x.X = c->dSinvF + off; x.XT = TWO ? nullptr : c->dSinvB + off;
           sv.push_back( x );
-          if ( LU ) { SinvTask y = x; y.P = Ub + m.lptr; y.inv64 = c->dInv2 + m.invptr; y.piv = nullptr; y.X = c->dSinvTmp + off; y.XT = c->dSinvB + off; sv.push_back( y ); }
+          if ( TWO ) { SinvTask y = x; y.P = Ub + m.lptr; y.inv64 = c->dInv2 + m.invptr; y.piv = nullptr; y.X = c->dSinvTmp + off; y.XT = c->dSinvB + off; sv.push_back( y ); }
         }
       }
     }
@@ -734,7 +762,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     for ( int d = 0; d <= S->maxdepth; d++ ) { small_rng[d].first = ( int64_t )sm.size(); for ( int s : levels[d] ) { if ( is_small( s ) ) sm.push_back( s ); else big[d].push_back( s ); } small_rng[d].second = ( int64_t )sm.size() - small_rng[d].first; }
     std::vector<SLaunch>& SS = c->slaunches;
     const double* Fb = c->dL;                       /* forward sweep: L */
-    const double* Mb = LU ? c->dU : c->dL;          /* backward sweep: L' x, or U x through the U' panels */
+    const double* Mb = TWO ? c->dU : c->dL;         /* backward sweep: L' x, or U x through the U' panels (L D L': U' = W = L D) */
     struct Mark { int64_t t, g; };
     auto mark = [&]( bool T ) { return Mark{ ( int64_t )( T ? tt.size() : tv.size() ), ( int64_t )tg.size() }; };
     auto add_task = [&]( const SvTask& x, bool T ) {
@@ -813,24 +841,24 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
 
 /* ------------------------------------------------------------- factor */
 static int run_factor( b200_ctx* c ) {
-  const bool LU = c->kind == B200_KIND_LU;
+  const bool LU = c->kind == B200_KIND_LU, LD = c->kind == B200_KIND_LDLT, TWO = LU || LD;
   cudaStream_t st = c->stream;
   CK( cudaEventRecord( c->ev0, st ) );
   CK( cudaMemsetAsync( c->dErr, 0, sizeof( int ), st ) );
   CK( cudaMemsetAsync( c->dPert, 0, sizeof( int ), st ) );
   CK( cudaMemsetAsync( c->dL, 0, ( size_t )c->lsize * 8, st ) );
-  if ( LU ) CK( cudaMemsetAsync( c->dU, 0, ( size_t )c->lsize * 8, st ) );
+  if ( TWO ) CK( cudaMemsetAsync( c->dU, 0, ( size_t )c->lsize * 8, st ) );
   if ( c->nnzA > 0 ) {
     const int blocks = ( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 16 );
     scatter_A_kernel<<<blocks, 256, 0, st>>>( c->dVals, c->amap.d, c->nnzA, c->dL, c->dU );
   }
-  if ( LU ) { /* static-pivot threshold sqrt(eps) * max|a_ij| */
+  if ( TWO ) { /* static-pivot threshold sqrt(eps) * max|a_ij| */
     CK( cudaMemsetAsync( c->dMaxBits, 0, 8, st ) );
     if ( c->nnzA > 0 ) maxabs_kernel<<<( int )std::min<int64_t>( ( c->nnzA + 255 ) / 256, 148 * 8 ), 256, 0, st>>>( c->dVals, c->nnzA, c->dMaxBits );
     tiny_from_max_kernel<<<1, 1, 0, st>>>( c->dMaxBits, c->dTiny );
   }
   if ( c->world > 1 ) { CK( cudaEventRecord( c->evs, st ) ); CK( cudaStreamWaitEvent( c->stream3, c->evs, 0 ) ); CK( cudaStreamWaitEvent( c->stream4, c->evs, 0 ) ); }   /* nothing may land in L before it has been zeroed and scattered */
-  int64_t nlaunch = 3 + ( LU ? 1 : 0 );
+  int64_t nlaunch = 3 + ( TWO ? 3 : 0 );
   double gemm_flops = 0; int64_t gemm_launches = 0;
   for ( int k = 0; k < LK_COUNT; k++ ) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
   int cur_depth = -1; size_t nlev = 0;
@@ -849,7 +877,8 @@ static int run_factor( b200_ctx* c ) {
         else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
         break;
       case LK_DIAG:
-        if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
+        if ( LD ) ldlt_diag_kernel<<<( unsigned )l.count, 256, LDLT_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
+        else if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
         else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
       case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;

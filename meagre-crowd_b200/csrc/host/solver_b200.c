@@ -11,7 +11,8 @@
  *   - errors: message on stderr + abort(), like the reference's assert()s
  *   - analyze/factorize/evaluate may be repeated on one state (-r N)
  * Tuning comes from the environment because the callbacks carry no options:
- *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_REFINE (steps; default automatic), B200_VERBOSE.
+ *   B200_DEVICE (default 0), B200_ND_LEAF, B200_NO_RELAX, B200_REFINE (steps; default automatic), B200_VERBOSE,
+ *   B200_SYM_KIND = cholesky | ldlt | lu  (symmetric input: default Cholesky, L D L' with Bunch-Kaufman pivots when a pivot is not positive).
  * There is no CPU fallback: without a usable GPU, init aborts.
  */
 #include <assert.h>
@@ -24,7 +25,7 @@ typedef struct {
   b200_ctx_t* ctx;
   b200_symbolic_t* sym;
   int kind;               /* kind of the current analysis */
-  int lu_fallback;        /* symmetric input that turned out not to be SPD */
+  int indefinite;         /* a symmetric input turned out not to be positive definite: later analyses of this state go straight to L D L' */
   /* full-matrix expansion used when a symmetric (upper) input goes through LU */
   unsigned int* fcolptr; unsigned int* frowidx; double* fvals; size_t* fsrc; size_t fnz;
   size_t n;
@@ -88,7 +89,7 @@ static void analyze_kind( solver_state_t* s, matrix_t* A, int kind ) {
   if ( b200_upload_symbolic( p->ctx, p->sym ) != B200_OK ) die( "upload of the symbolic structure failed" );
   if ( s->verbosity >= 3 || getenv( "B200_VERBOSE" ) )
     fprintf( stderr, "b200: n=%d kind=%s nnz(L)=%lld (stored %lld) flops=%.4g supernodes=%d (fundamental %d) levels=%d maxfront=%d order=%.3fs symbolic=%.3fs\n",
-             p->sym->n, kind == B200_KIND_LU ? "LU" : "Cholesky", ( long long )p->sym->nnzL, ( long long )p->sym->stored_nnzL,
+             p->sym->n, kind == B200_KIND_LU ? "LU" : kind == B200_KIND_LDLT ? "LDLT" : "Cholesky", ( long long )p->sym->nnzL, ( long long )p->sym->stored_nnzL,
              p->sym->flops * ( kind == B200_KIND_LU ? 2 : 1 ), p->sym->ns, p->sym->nfund, p->sym->maxdepth + 1, p->sym->maxfront, p->sym->t_order, p->sym->t_symbolic );
 }
 
@@ -102,8 +103,10 @@ void solver_analyze_b200( solver_state_t* s, matrix_t* A ) {
   assert( A->format == SM_CSC && A->base == FIRST_INDEX_ZERO && A->data_type == REAL_DOUBLE );
   assert( A->m == A->n );
   assert( A->sym == SM_UNSYMMETRIC || ( A->sym == SM_SYMMETRIC && A->location == UPPER_TRIANGULAR ) );
-  p->lu_fallback = 0;
-  analyze_kind( s, A, A->sym == SM_SYMMETRIC ? B200_KIND_CHOLESKY : B200_KIND_LU );
+  int kind = A->sym == SM_SYMMETRIC ? ( p->indefinite ? B200_KIND_LDLT : B200_KIND_CHOLESKY ) : B200_KIND_LU;
+  const char* sk = getenv( "B200_SYM_KIND" );
+  if ( sk && A->sym == SM_SYMMETRIC ) kind = strcmp( sk, "ldlt" ) == 0 ? B200_KIND_LDLT : strcmp( sk, "lu" ) == 0 ? B200_KIND_LU : B200_KIND_CHOLESKY;
+  analyze_kind( s, A, kind );
 }
 
 void solver_factorize_b200( solver_state_t* s, matrix_t* A ) {
@@ -117,12 +120,19 @@ void solver_factorize_b200( solver_state_t* s, matrix_t* A ) {
   if ( p->kind == B200_KIND_CHOLESKY ) {
     r = b200_factor_host( p->ctx, A->dd );
     if ( r == B200_ERR_NOT_SPD ) {
-      /* symmetric but not positive definite (tests/sym.mm): redo as LU on the full matrix */
-      if ( s->verbosity >= 3 || getenv( "B200_VERBOSE" ) ) fprintf( stderr, "b200: %s -- falling back to LU\n", b200_last_error() );
-      p->lu_fallback = 1;
-      analyze_kind( s, A, B200_KIND_LU );
+      /* symmetric but not positive definite (tests/sym.mm, which the reference runs on its general backends, testsuite.at:325-329):
+       * the SAME analysis serves L D L' -- only the numeric schedule is rebuilt, with pivoting diagonal blocks and the second panel */
+      if ( s->verbosity >= 3 || getenv( "B200_VERBOSE" ) ) fprintf( stderr, "b200: %s -- switching to LDL'\n", b200_last_error() );
+      p->indefinite = 1;
+      p->sym->kind = B200_KIND_LDLT; p->kind = B200_KIND_LDLT;
+      if ( b200_upload_symbolic( p->ctx, p->sym ) != B200_OK ) die( "upload of the symbolic structure failed" );
     } else if ( r != B200_OK ) die( "factorization failed" );
     else return;
+  }
+  if ( p->kind == B200_KIND_LDLT ) {
+    r = b200_factor_host( p->ctx, A->dd );
+    if ( r != B200_OK ) die( "LDL' factorization failed" );
+    return;
   }
   const double* vals = A->dd;
   if ( A->sym == SM_SYMMETRIC ) { /* LU of a symmetric input: values follow the expansion */

@@ -28,6 +28,7 @@ def lib():
         L = C.CDLL(LIB)
         ip, dp, lp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int64)
         L.oracle_dense_solve.argtypes = [C.c_int, dp, dp, C.c_int, dp]
+        L.oracle_ldlt_solve.argtypes = [C.c_int, dp, dp, C.c_int, dp]
         L.oracle_etree.argtypes = [C.c_int, ip, ip, ip]
         L.oracle_chol_uplooking.restype = C.c_int64
         L.oracle_chol_uplooking.argtypes = [C.c_int, ip, ip, dp, ip, ip, lp, ip, dp]
@@ -50,6 +51,17 @@ def dense_solve(A, b):
     r = lib().oracle_dense_solve(A.shape[0], _p(A, C.c_double), _p(b2, C.c_double), b2.shape[1], _p(x, C.c_double))
     if r != 0:
         raise ZeroDivisionError("singular matrix")
+    return x.reshape(np.shape(b)) if np.ndim(b) == 1 else x
+
+
+def ldlt_solve(A, b):
+    """dense symmetric indefinite solve by Bunch-Kaufman L D L' (A full symmetric)"""
+    A = np.asfortranarray(A, dtype=np.float64)
+    b2 = np.asfortranarray(np.asarray(b, dtype=np.float64).reshape(A.shape[0], -1))
+    x = np.empty_like(b2, order="F")
+    r = lib().oracle_ldlt_solve(A.shape[0], _p(A, C.c_double), _p(b2, C.c_double), b2.shape[1], _p(x, C.c_double))
+    if r != 0:
+        raise ZeroDivisionError(f"column {r - 1} is exactly zero")
     return x.reshape(np.shape(b)) if np.ndim(b) == 1 else x
 
 

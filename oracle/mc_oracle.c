@@ -64,6 +64,75 @@ int oracle_dense_solve( int n, const double* A, const double* b, int p, double* 
   return 0;
 }
 
+/* ------------------------------------- dense symmetric indefinite solve: P A P' = L D L'
+ * Bunch-Kaufman partial pivoting (1x1 / 2x2 pivots, alpha = (1+sqrt(17))/8), the published algorithm behind LAPACK dsytf2 and
+ * the symmetric-indefinite mode of the reference's MUMPS backend (SYM=2, src/solver_mumps.c:44-51; the reference's tests run
+ * tests/sym.mm on its general backends, testsuite.at:325-329).  A: n x n column-major, full symmetric; b, x: n x p column-major.
+ * Pivots are searched over the WHOLE remaining matrix here; the device path restricts them to a diagonal block and perturbs,
+ * so agreement of the solutions is what the tests check.  Returns 0, or j+1 if column j is exactly zero. */
+int oracle_ldlt_solve( int n, const double* A, const double* b, int p, double* x ) {
+  const double alpha = ( 1.0 + sqrt( 17.0 ) ) / 8.0;
+  double* M = malloc( sizeof( double ) * ( size_t )n * n ); memcpy( M, A, sizeof( double ) * ( size_t )n * n );
+  int* sig = malloc( sizeof( int ) * n ); int* two = calloc( n, sizeof( int ) );
+  for ( int i = 0; i < n; i++ ) sig[i] = i;
+#define AT( r, c ) M[( r ) + ( size_t )( c ) * n]
+  int j = 0, ret = 0;
+  while ( j < n ) {
+    double colmax = 0; int imax = j;
+    for ( int i = j + 1; i < n; i++ ) if ( fabs( AT( i, j ) ) > colmax ) { colmax = fabs( AT( i, j ) ); imax = i; }
+    const double absakk = fabs( AT( j, j ) );
+    int kp = j, step = 1;
+    if ( absakk == 0.0 && colmax == 0.0 ) { ret = j + 1; break; }
+    if ( absakk < alpha * colmax ) {
+      double rowmax = 0;
+      for ( int q = j; q < n; q++ ) if ( q != imax ) { const double v = fabs( q < imax ? AT( imax, q ) : AT( q, imax ) ); if ( v > rowmax ) rowmax = v; }
+      if ( absakk * rowmax >= alpha * colmax * colmax ) kp = j;
+      else if ( fabs( AT( imax, imax ) ) >= alpha * rowmax ) kp = imax;
+      else { kp = imax; step = 2; }
+    }
+    const int kk = j + step - 1;
+    if ( kp != kk ) { /* symmetric interchange on the lower triangle (and on the computed columns of L) */
+      for ( int c = 0; c < kk; c++ ) { const double t = AT( kk, c ); AT( kk, c ) = AT( kp, c ); AT( kp, c ) = t; }
+      for ( int r = kk + 1; r < kp; r++ ) { const double t = AT( r, kk ); AT( r, kk ) = AT( kp, r ); AT( kp, r ) = t; }
+      for ( int r = kp + 1; r < n; r++ ) { const double t = AT( r, kk ); AT( r, kk ) = AT( r, kp ); AT( r, kp ) = t; }
+      { const double t = AT( kk, kk ); AT( kk, kk ) = AT( kp, kp ); AT( kp, kp ) = t; }
+      { const int t = sig[kk]; sig[kk] = sig[kp]; sig[kp] = t; }
+    }
+    if ( step == 1 ) {
+      const double d = AT( j, j );
+      for ( int c = j + 1; c < n; c++ ) { const double l = AT( c, j ) / d; for ( int r = c; r < n; r++ ) AT( r, c ) -= AT( r, j ) * l; }
+      for ( int r = j + 1; r < n; r++ ) AT( r, j ) /= d;
+      j += 1;
+    } else {
+      two[j] = 1;
+      const double d21 = AT( j + 1, j ), e11 = AT( j, j ) / d21, e22 = AT( j + 1, j + 1 ) / d21, sc = 1.0 / ( ( e11 * e22 - 1.0 ) * d21 );
+      for ( int c = j + 2; c < n; c++ ) {
+        const double l1 = sc * ( e22 * AT( c, j ) - AT( c, j + 1 ) ), l2 = sc * ( e11 * AT( c, j + 1 ) - AT( c, j ) );
+        for ( int r = c; r < n; r++ ) AT( r, c ) -= AT( r, j ) * l1 + AT( r, j + 1 ) * l2;
+      }
+      for ( int r = j + 2; r < n; r++ ) { const double a1 = AT( r, j ), a2 = AT( r, j + 1 ); AT( r, j ) = sc * ( e22 * a1 - a2 ); AT( r, j + 1 ) = sc * ( e11 * a2 - a1 ); }
+      j += 2;
+    }
+  }
+  if ( ret == 0 ) {
+    double* y = malloc( sizeof( double ) * n );
+    for ( int c = 0; c < p; c++ ) {
+      for ( int i = 0; i < n; i++ ) y[i] = b[sig[i] + ( size_t )c * n];
+      for ( int q = 0; q < n; q++ ) { const int w = two[q] ? 2 : 1; for ( int e = 0; e < w; e++ ) for ( int r = q + w; r < n; r++ ) y[r] -= AT( r, q + e ) * y[q + e]; q += w - 1; }
+      for ( int q = 0; q < n; q++ ) {
+        if ( two[q] ) { const double d21 = AT( q + 1, q ), e11 = AT( q, q ) / d21, e22 = AT( q + 1, q + 1 ) / d21, sc = 1.0 / ( ( e11 * e22 - 1.0 ) * d21 ); const double a = y[q], bb = y[q + 1]; y[q] = sc * ( e22 * a - bb ); y[q + 1] = sc * ( e11 * bb - a ); q++; }
+        else y[q] /= AT( q, q );
+      }
+      for ( int q = n - 1; q >= 0; q-- ) { const int lo = ( q > 0 && two[q - 1] ) ? q - 1 : q; const int w = q - lo + 1; for ( int e = 0; e < w; e++ ) { double v = y[lo + e]; for ( int r = lo + w; r < n; r++ ) v -= AT( r, lo + e ) * y[r]; y[lo + e] = v; } q = lo; }
+      for ( int i = 0; i < n; i++ ) x[sig[i] + ( size_t )c * n] = y[i];
+    }
+    free( y );
+  }
+#undef AT
+  free( M ); free( sig ); free( two );
+  return ret;
+}
+
 /* ------------------------------------------------------- etree (Liu 1990)
  * cp/ri: CSC of the symmetric matrix, only entries with row < col are read */
 void oracle_etree( int n, const int* cp, const int* ri, int* parent ) {

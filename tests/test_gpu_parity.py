@@ -229,6 +229,106 @@ def test_not_positive_definite_is_reported_not_hidden(mc, golden):
     s.close()
 
 
+def shifted_laplacian(nx, ny, nz, shift):
+    """3-D 7-point Laplacian minus shift*I: symmetric indefinite when the shift lies inside the spectrum (0, 12)"""
+    n, cp, ri, v = stencils.poisson3d_upper(nx, ny, nz)
+    diag = ri.astype(np.int64) == np.repeat(np.arange(n), np.diff(cp.astype(np.int64)))
+    v = v.copy(); v[diag] -= shift
+    return n, cp, ri, v
+
+
+@pytest.mark.parametrize("rhs,tol", [("default", 5e-14), ("rhs1", 5e-14)])
+def test_ldlt_reproduces_sym_fixture(mc, golden, rhs, tol):
+    """tests/sym.mm (indefinite) through kind = LDLT of the shim: testsuite.at:325-329 at the reference's tolerance"""
+    Ad = read_mm_dense(f"{golden}/sym.mm")
+    U = sp.triu(sp.csc_matrix(Ad)).tocsc(); U.sort_indices()
+    s = mc.Solver(); s.analyze(5, U.indptr, U.indices, mc.KIND_LDLT)
+    assert s.factor(U.data) == 0, s.err()
+    assert s.stats().npiv_perturbed == 0
+    b = np.arange(5.0) if rhs == "default" else read_mm_dense(f"{golden}/rhs1.mm")[:, 0]
+    x = s.solve(b)
+    assert np.all(np.abs(x - read_mm_dense(f"{golden}/sym-{rhs}-ans.mm")[:, 0]) <= tol)
+    s.close()
+
+
+def test_plugin_routes_indefinite_symmetric_input_through_ldlt(mc, golden, capfd):
+    """the plugin tries Cholesky, sees a non-positive pivot and switches the SAME analysis to L D L' (no LU re-analysis)"""
+    os.environ["B200_VERBOSE"] = "1"
+    try:
+        x, _ = plugin_solve(mc, f"{golden}/sym.mm", rep=2)
+    finally:
+        del os.environ["B200_VERBOSE"]
+    err = capfd.readouterr().err
+    assert "switching to LDL'" in err and "kind=LDLT" in err and "kind=LU" not in err
+    assert np.all(np.abs(x - read_mm_dense(f"{golden}/sym-default-ans.mm")) <= 5e-14)
+
+
+@pytest.mark.parametrize("dims,shift", [((12, 12, 12), 3.3), ((30, 29, 31), 5.1), ((20, 7, 5), 11.0)])
+def test_ldlt_indefinite_grids_vs_oracles(mc, dims, shift):
+    """shifted Laplacians (eigenvalues of both signs): dense Bunch-Kaufman oracle where it finishes, SuperLU otherwise; several
+    64-blocks per supernode, 1 / 3 / 9 right-hand sides (FMA and tensor sweeps) with identical bits per column"""
+    import scipy.sparse.linalg as sla
+    n, cp, ri, v = shifted_laplacian(*dims, shift)
+    A = stencils.to_scipy(n, cp, ri, v, True)
+    s = mc.Solver(); s.analyze(n, cp, ri, mc.KIND_LDLT)
+    assert s.factor(v) == 0, s.err()
+    rng = np.random.default_rng(5); B = rng.standard_normal((n, 9))
+    X = s.solve(B)
+    assert np.array_equal(X[:, 4], s.solve(B[:, 4].copy())) and np.array_equal(X[:, :3], s.solve(B[:, :3].copy()))
+    for c in range(9):
+        assert backward_error(A, X[:, c], B[:, c]) <= 1e-12
+    Xr = oracle.ldlt_solve(A.toarray(), B) if n <= 2000 else sla.splu(A.tocsc()).solve(B)
+    assert np.abs(X - Xr).max() <= 1e-8 * np.abs(Xr).max()
+    s.close()
+
+
+def test_ldlt_indefinite_at_64cubed(mc):
+    """a 3-D indefinite system at a size no scalar oracle reaches: backward error <= 1e-12 (the north_star bound), no perturbed pivot,
+    the factorization repeatable bit for bit, inertia-free checksum  sum_j ||L(:,j)||^2 finite"""
+    n, cp, ri, v = shifted_laplacian(64, 64, 64, 2.7)
+    A = stencils.to_scipy(n, cp, ri, v, True)
+    s = mc.Solver(); s.analyze(n, cp, ri, mc.KIND_LDLT)
+    assert s.factor(v) == 0, s.err()
+    st = s.stats()
+    b = np.arange(n, dtype=float)
+    x = s.solve(b)
+    assert backward_error(A, x, b) <= 1e-12
+    assert s.stats().npiv_perturbed == 0
+    cs = s.colnorms(); assert np.all(np.isfinite(cs))
+    assert s.factor(v) == 0 and np.array_equal(cs, s.colnorms())
+    print(f"LDLT 64^3: factor {st.factor_ms:.1f} ms, refine_steps {s.stats().refine_steps}")
+    s.close()
+
+
+def test_ldlt_on_a_positive_definite_matrix_equals_cholesky(mc):
+    """on an SPD system no interchange happens: L D L' and L L' give the same solution to rounding"""
+    n, cp, ri, v = stencils.poisson3d_upper(16)
+    b = np.arange(n, dtype=float)
+    xs = []
+    for kind in (mc.KIND_CHOLESKY, mc.KIND_LDLT):
+        s = mc.Solver(); s.analyze(n, cp, ri, kind); assert s.factor(v) == 0; xs.append(s.solve(b)); s.close()
+    assert np.abs(xs[0] - xs[1]).max() <= 1e-12 * np.abs(xs[0]).max()
+
+
+def test_ldlt_saddle_point_zero_diagonal_block(mc):
+    """KKT matrix [[K, B'], [B, 0]]: zero diagonal entries need 2x2 pivots (or a perturbation that refinement repairs)"""
+    rng = np.random.default_rng(2)
+    n1, cp, ri, v = stencils.poisson2d_upper(20)
+    K = stencils.to_scipy(n1, cp, ri, v, True)
+    Bm = sp.random(60, n1, density=0.02, random_state=4, format="csr") + sp.eye(60, n1, format="csr")
+    A = sp.bmat([[K, Bm.T], [Bm, None]], format="csc")
+    n = A.shape[0]
+    U = sp.triu(A, 0).tocsc(); U.sort_indices()
+    s = mc.Solver(); s.analyze(n, U.indptr, U.indices, mc.KIND_LDLT)
+    assert s.factor(U.data) == 0, s.err()
+    b = rng.standard_normal(n)
+    x = s.solve(b)
+    assert backward_error(A, x, b) <= 1e-12
+    xo = oracle.ldlt_solve(A.toarray(), b)
+    assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max()
+    s.close()
+
+
 LU_CASES = [("cd27-6", lambda: stencils.convdiff27_full(6)), ("cd27-12x9x7", lambda: stencils.convdiff27_full(12, 9, 7)),
             ("cd27-16", lambda: stencils.convdiff27_full(16)), ("p3d-full-10", lambda: stencils.upper_to_full(*stencils.poisson3d_upper(10)))]
 

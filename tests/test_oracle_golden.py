@@ -69,12 +69,22 @@ def test_oracle_multifrontal_matches_uplooking(mc):
     mc.lib().b200_symbolic_free(S)
 
 
-def _unused_sym_dict(mc, S):
-    s = S.contents
-    ns, n = s.ns, s.n
-    d = dict(ns=ns, n=n, maxdepth=s.maxdepth)
-    for name, ln, dt in (("perm", n, np.int32), ("iperm", n, np.int32), ("sn_start", ns + 1, np.int32), ("sn_parent", ns, np.int32),
-                         ("sn_depth", ns, np.int32), ("rowptr", ns + 1, np.int64), ("lptr", ns + 1, np.int64)):
-        d[name] = mc.sym_array(S, name, ln, dt)
-    d["rowidx"] = mc.sym_array(S, "rowidx", int(d["rowptr"][-1]), np.int32)
-    return d
+@pytest.mark.parametrize("rhs", ["default", "rhs1"])
+def test_oracle_ldlt_reproduces_sym_answers(golden, rhs):
+    """tests/sym.mm is symmetric indefinite: the Bunch-Kaufman L D L' oracle must land on the reference's answers (5e-14)"""
+    A = read_mm_dense(f"{golden}/sym.mm")
+    assert np.array_equal(A, A.T) and np.linalg.eigvalsh(A).min() < 0 < np.linalg.eigvalsh(A).max()
+    b = np.arange(5.0) if rhs == "default" else read_mm_dense(f"{golden}/rhs1.mm")[:, 0]
+    e = read_mm_dense(f"{golden}/sym-{rhs}-ans.mm")[:, 0]
+    assert np.all(np.abs(oracle.ldlt_solve(A, b) - e) <= 5e-14)
+
+
+def test_oracle_ldlt_needs_2x2_pivots_and_agrees_with_lu():
+    """zero diagonal (a saddle-point matrix): only 2x2 pivots factor it; answer against the dense LU oracle"""
+    rng = np.random.default_rng(3)
+    K = rng.standard_normal((12, 12)); K = K @ K.T + 12 * np.eye(12); B = rng.standard_normal((5, 12))
+    A = np.block([[K, B.T], [B, np.zeros((5, 5))]])
+    P = rng.permutation(17); A = A[np.ix_(P, P)]
+    b = rng.standard_normal((17, 2))
+    assert np.abs(oracle.ldlt_solve(A, b) - oracle.dense_solve(A, b)).max() <= 1e-12
+
