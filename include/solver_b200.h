@@ -201,6 +201,9 @@ typedef struct b200_stats {
   double backward_error;   /* componentwise backward error seen before the last decision (automatic mode), else -1 */
   double first_backward_error;  /* the same quantity for the unrefined solution (automatic mode), else -1 */
   double comm_bytes;       /* multi-GPU: bytes this rank sends + receives over NCCL per factorization (0 on one GPU) */
+  double lu_max_multiplier;       /* LU: largest |l(i,j)| over the fully-summed rows of all fronts (1 inside a diagonal block by construction) */
+  double pivot_threshold;         /* LU: the threshold u the multipliers are checked against (default 0.1, env B200_PIVOT_THRESHOLD)            */
+  int npiv_threshold_violations;  /* LU: multipliers above 1/u, i.e. pivots that threshold partial pivoting over the whole front would have refused */
 } b200_stats_t;
 int b200_get_stats( b200_ctx_t* c, b200_stats_t* out );
 /* per-kernel timing of the next factor (serialises launches; diagnostics only) */

@@ -60,7 +60,8 @@ class b200_symbolic_t(C.Structure):
 class b200_stats_t(C.Structure):
     _fields_ = [("factor_ms", C.c_double), ("solve_ms", C.c_double), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double), ("gemm_alg_flops", C.c_double),
                 ("launches", C.c_int64), ("solve_launches", C.c_int64), ("gemm_launches", C.c_int64),
-                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("device_bytes", C.c_int64), ("npiv_perturbed", C.c_int), ("refine_steps", C.c_int), ("backward_error", C.c_double), ("first_backward_error", C.c_double), ("comm_bytes", C.c_double)]
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("device_bytes", C.c_int64), ("npiv_perturbed", C.c_int), ("refine_steps", C.c_int), ("backward_error", C.c_double), ("first_backward_error", C.c_double), ("comm_bytes", C.c_double),
+                ("lu_max_multiplier", C.c_double), ("pivot_threshold", C.c_double), ("npiv_threshold_violations", C.c_int)]
 
 
 class b200_plan_t(C.Structure):

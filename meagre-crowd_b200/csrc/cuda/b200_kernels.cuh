@@ -400,7 +400,7 @@ __global__ void __launch_bounds__( 256 ) small_front_kernel( const int* __restri
  * rows.  piv[j] = block-local row swapped into position j.  Tiny pivots are
  * replaced by +-tiny (static perturbation) and counted.  Outputs: packed L\U
  * in place, inv = inverse of unit-lower L, inv2 = (inverse of U) transposed. */
-__global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed ) {
+__global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed, int* __restrict__ err ) {
   const double tiny = *tiny_p;
   extern __shared__ double dsm[];
   double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );
@@ -428,6 +428,7 @@ __global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __re
     if ( p != j && tid < nb ) { double tmp = a[j][tid]; a[j][tid] = a[p][tid]; a[p][tid] = tmp; }
     __syncthreads();
     double d = a[j][j];
+    if ( d != d && tid == 0 ) atomicCAS( err, 0, -( t.col + j + 1 ) );      /* NaN pivot column: the factorization cannot be repaired by a perturbation */
     if ( !( fabs( d ) > tiny ) ) { d = ( d < 0.0 ) ? -tiny : tiny; if ( tid == 0 ) { a[j][j] = d; atomicAdd( nperturbed, 1 ); } }
     if ( tid < nb ) { colv[tid] = tid > j ? a[tid][j] / d : 0.0; rowv[tid] = tid > j ? a[j][tid] : 0.0; }
     __syncthreads();
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __re
  * Both are full nb x nb matrices (the interchanges are folded in as a column permutation).  The panels' diagonal blocks receive
  * L (unit lower, pivot order) and D (block diagonal, lower part); nothing reads them again. */
 constexpr int LDLT_SMEM = ( 3 * NB * ( NB + 1 ) + 2 * NB ) * 8 + 3 * NB * 4;
-__global__ void __launch_bounds__( 256 ) ldlt_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed ) {
+__global__ void __launch_bounds__( 256 ) ldlt_diag_kernel( const DiagTask* __restrict__ tasks, const double* __restrict__ tiny_p, int* __restrict__ nperturbed, int* __restrict__ err ) {
   extern __shared__ double dsm[];
   double ( *a )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm );                          /* full symmetric active matrix; columns < j hold L */
   double ( *x )[NB + 1] = reinterpret_cast<double ( * )[NB + 1]>( dsm + NB * ( NB + 1 ) );          /* inv(L)                                         */
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__( 256 ) ldlt_diag_kernel( const DiagTask* __res
       for ( int i = j + 1 + lane; i < nb; i += 32 ) { const double v = fabs( a[i][j] ); if ( v > colmax ) { colmax = v; imax = i; } }
       for ( int o = 16; o; o >>= 1 ) { const double ov = __shfl_xor_sync( 0xffffffffu, colmax, o ); const int oi = __shfl_xor_sync( 0xffffffffu, imax, o ); if ( ov > colmax || ( ov == colmax && ov > 0.0 && oi < imax ) ) { colmax = ov; imax = oi; } }
       const double absakk = fabs( a[j][j] );
+      if ( lane == 0 && ( absakk != absakk || colmax != colmax ) ) atomicCAS( err, 0, -( t.col + j + 1 ) );      /* NaN in the pivot column */
       int kp = j, step = 1;
       if ( !( fmax( absakk, colmax ) > tiny ) ) {                  /* nothing usable in this column: static perturbation (also catches NaN) */
         if ( lane == 0 ) { a[j][j] = ( a[j][j] < 0.0 ) ? -tiny : tiny; atomicAdd( nperturbed, 1 ); }
@@ -1667,6 +1669,25 @@ __global__ void __launch_bounds__( 256 ) panel_colnorm_kernel( const SnMeta* __r
       if ( lane == 0 ) out[S.c0 + j] = acc;
     }
   }
+}
+
+/* LU: verification of threshold partial pivoting over ALL fully-summed rows of every front.  The diagonal-block kernel pivots inside its
+ * 64 rows (|l| <= 1 there); for the fully-summed rows below the block, l(i,j) = a~(i,j) / u(j,j), so  |u(j,j)| >= u * |a~(i,j)|  (the
+ * acceptance test of threshold pivoting, UMFPACK / MUMPS) holds for every candidate row exactly when  max |l(i,j)| <= 1/u.
+ * One pass over the pivot blocks of the finished L panels: largest multiplier, and how many exceed the bound. */
+__global__ void __launch_bounds__( 256 ) lu_growth_kernel( const SnMeta* __restrict__ sn, int ns, const double* __restrict__ L, double bound,
+                                                           unsigned long long* __restrict__ max_bits, int* __restrict__ nviol ) {
+  double mx = 0.0; int nv = 0;
+  for ( int s = blockIdx.x; s < ns; s += gridDim.x ) {
+    const SnMeta S = sn[s];
+    if ( S.k <= NB ) continue;
+    for ( int j = threadIdx.x >> 5; j < S.k; j += 8 ) {
+      const double* col = L + S.lptr + ( int64_t )j * S.ld;
+      for ( int i = ( j / NB + 1 ) * NB + ( threadIdx.x & 31 ); i < S.k; i += 32 ) { const double v = fabs( col[i] ); if ( !( v <= bound ) ) nv++; if ( v > mx || v != v ) mx = v != v ? CUDART_INF : v; }
+    }
+  }
+  for ( int o = 16; o; o >>= 1 ) { mx = fmax( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) ); nv += __shfl_xor_sync( 0xffffffffu, nv, o ); }
+  if ( ( threadIdx.x & 31 ) == 0 ) { if ( mx > 0.0 ) atomicMax( max_bits, ( unsigned long long )__double_as_longlong( mx ) ); if ( nv ) atomicAdd( nviol, nv ); }
 }
 
 /* micro-benchmark: issue-rate roof of DMMA.8x8x4 (registers only, 16 independent accumulators per warp) */

@@ -131,7 +131,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; bool use_bulk = true, use_pers = false, use_small_front = true; DevVec<int> small_sns; int pers_grid = 444;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; int* dViol = nullptr; double pivot_threshold = 0.1; bool use_bulk = true, use_pers = false, use_small_front = true, replicate = false; DevVec<int> small_sns; int pers_grid = 444;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -179,7 +179,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
     CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); }
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) ); CKN( cudaEventCreateWithFlags( &c->evs2, cudaEventDisableTiming ) );
-  CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) );
+  CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) ); CKN( cudaMalloc( &c->dViol, sizeof( int ) ) );
+  { const char* e = getenv( "B200_PIVOT_THRESHOLD" ); if ( e && atof( e ) > 0.0 && atof( e ) <= 1.0 ) c->pivot_threshold = atof( e ); }
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_pers_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
@@ -191,6 +192,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
   CKN( cudaFuncSetAttribute( small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM ) );
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
+  c->replicate = getenv( "B200_REPLICATE_FACTOR" ) != nullptr;
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
   CKN( cudaFuncSetAttribute( sv_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_gemv_smem<4>() ) );
@@ -237,7 +239,7 @@ extern "C" int b200_mg_rank( b200_ctx_t* c, int* rank, int* world ) { if ( !c ) 
 extern "C" b200_ctx_t* b200_ctx_create_dry( int rank, int world ) {
   if ( world < 1 || rank < 0 || rank >= world ) return nullptr;
   b200_ctx* c = new b200_ctx();
-  c->dry = true; c->rank = rank; c->world = world;
+  c->dry = true; c->rank = rank; c->world = world; c->replicate = getenv( "B200_REPLICATE_FACTOR" ) != nullptr;
   memset( &c->stats, 0, sizeof( c->stats ) );
   memset( &c->prop, 0, sizeof( c->prop ) ); c->prop.multiProcessorCount = 148;
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
@@ -271,7 +273,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   cudaSetDevice( c->device );
   cudaStreamSynchronize( c->stream ); cudaStreamSynchronize( c->stream2 ); cudaStreamSynchronize( c->stream3 ); cudaStreamSynchronize( c->stream4 );   /* pending NCCL sends read dL / dInv */
   release_symbolic( c );
-  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dTiny ); cudaFree( c->dMaxBits ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
+  cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dTiny ); cudaFree( c->dMaxBits ); cudaFree( c->dViol ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs ); cudaEventDestroy( c->evs2 );
   for ( cudaEvent_t e : c->events ) cudaEventDestroy( e );
   for ( cudaEvent_t e : c->lvl_ev ) cudaEventDestroy( e );
@@ -696,15 +698,16 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         }
       }
     }
-    if ( MG ) { /* replicate what has become final on this level: every rank ends up with the whole factor (L panels and
-                 * diagonal-block inverses) for the sweeps.  Bulk traffic has its own communicator and stream so that it
-                 * never queues in front of a panel on the critical path. */
+    if ( MG ) { /* collect what has become final on this level on the SOLVE ROOT (rank 0): it ends up with the whole factor (L panels and
+                 * diagonal-block inverses) and runs the sweeps.  (Round 1 replicated the factor on every rank: 72 % of all NVLink bytes
+                 * at 8 GPUs, in competition with the panel broadcasts of the critical path; B200_REPLICATE_FACTOR=1 restores that.)
+                 * Bulk traffic has its own communicator and stream so that it never queues in front of a panel. */
       const int64_t m0 = ( int64_t )MS.size();
       for ( const Run& rn : runs ) {
         if ( rn.ready != d ) continue;
         const int64_t lo = meta[rn.s0].lptr, lcnt = S->lptr[rn.s1 + 1] - lo;
         const int64_t io = meta[rn.s0].invptr, icnt = ( rn.s1 + 1 < ns ? meta[rn.s1 + 1].invptr : c->invsize ) - io;
-        for ( int r = 0; r < c->world; r++ ) {
+        for ( int r = 0; r < ( c->replicate ? c->world : 1 ); r++ ) {
           if ( r >= rn.h0 && r < rn.h0 + rn.hn ) continue;
           if ( me != rn.h0 && me != r ) continue;
           if ( lcnt > 0 ) { MS.push_back( { rn.h0, r, 0, lo, lcnt } ); c->comm_bytes += ( double )lcnt * 8.0; }
@@ -877,8 +880,8 @@ static int run_factor( b200_ctx* c ) {
         else extend_add_kernel<false><<<( unsigned )l.count, 256, 0, ls>>>( c->asm_tasks.d + l.first, c->sn.d, c->child_list.d, c->relidx.d, c->dL, c->dU, c->dCB[l.depth & 1], c->dCB[( l.depth + 1 ) & 1] );
         break;
       case LK_DIAG:
-        if ( LD ) ldlt_diag_kernel<<<( unsigned )l.count, 256, LDLT_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
-        else if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert );
+        if ( LD ) ldlt_diag_kernel<<<( unsigned )l.count, 256, LDLT_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert, c->dErr );
+        else if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert, c->dErr );
         else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
       case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;
@@ -919,13 +922,20 @@ static int run_factor( b200_ctx* c ) {
     }
   }
   /* explicit inverses of the solve blocks (feeds the sweeps; part of the factorization time) */
-  if ( c->sinv_tasks.n ) { build_sinv_kernel<<<( unsigned )c->sinv_tasks.n, 256, SINV_SMEM, st>>>( c->sinv_tasks.d ); nlaunch++; }
+  if ( c->sinv_tasks.n && ( c->world == 1 || c->rank == 0 || c->replicate ) ) { build_sinv_kernel<<<( unsigned )c->sinv_tasks.n, 256, SINV_SMEM, st>>>( c->sinv_tasks.d ); nlaunch++; }
+  int nviol = 0; unsigned long long gbits = 0;
+  if ( LU ) { /* threshold partial pivoting verified over all fully-summed rows (part of the factorization time) */
+    CK( cudaMemsetAsync( c->dMaxBits, 0, 8, st ) ); CK( cudaMemsetAsync( c->dViol, 0, sizeof( int ), st ) );
+    lu_growth_kernel<<<148 * 8, 256, 0, st>>>( c->sn.d, c->ns, c->dL, 1.0 / c->pivot_threshold, c->dMaxBits, c->dViol ); nlaunch++;
+  }
   CK( cudaEventRecord( c->ev1, st ) );
   CK( cudaGetLastError() );
   int err = 0, pert = 0;
   CK( cudaMemcpyAsync( &err, c->dErr, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
   CK( cudaMemcpyAsync( &pert, c->dPert, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  if ( LU ) { CK( cudaMemcpyAsync( &nviol, c->dViol, sizeof( int ), cudaMemcpyDeviceToHost, st ) ); CK( cudaMemcpyAsync( &gbits, c->dMaxBits, 8, cudaMemcpyDeviceToHost, st ) ); }
   CK( cudaStreamSynchronize( st ) );
+  { double g; memcpy( &g, &gbits, 8 ); c->stats.lu_max_multiplier = LU ? std::max( g, c->ns > 0 ? 1.0 : 0.0 ) : 0.0; c->stats.npiv_threshold_violations = nviol; c->stats.pivot_threshold = LU ? c->pivot_threshold : 0.0; }
   float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
   c->lvl_ms.assign( nlev, 0.f );
   for ( size_t i = 0; i < nlev; i++ ) { cudaEvent_t nx = i + 1 < nlev ? c->lvl_ev[i + 1] : c->ev1; cudaEventElapsedTime( &c->lvl_ms[i], c->lvl_ev[i], nx ); }
@@ -933,6 +943,7 @@ static int run_factor( b200_ctx* c ) {
   c->stats.gemm_alg_flops = c->gemm_alg_flops * ( c->flops_stored > 0 ? c->flops_exact / c->flops_stored : 1.0 );
   c->stats.gemm_ms = c->profile ? c->prof_ms[LK_GEMM_BIG] : 0.0;
   c->stats.npiv_perturbed = pert; c->stats.device_bytes = c->device_bytes; c->stats.comm_bytes = c->comm_bytes;
+  if ( err < 0 ) { char a[64]; snprintf( a, 64, "%d", -err - 1 ); set_err( "NaN in pivot column %s of the permuted matrix: the matrix is singular or holds non-finite values%s", a, "" ); c->factored = false; return B200_ERR_SINGULAR; }
   if ( err != 0 ) { char a[64]; snprintf( a, 64, "%d", err - 1 ); set_err( "matrix is not positive definite (pivot column %s of the permuted matrix)%s", a, "" ); c->factored = false; return B200_ERR_NOT_SPD; }
   c->factored = true;
   return B200_OK;
@@ -1090,8 +1101,10 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
   return B200_OK;
 }
 
+static bool holds_factor( const b200_ctx* c ) { return c->world == 1 || c->rank == 0 || c->replicate; }
 extern "C" int b200_solve_device( b200_ctx_t* c, const double* d_b, int p, double* d_x ) {
   if ( !c || !c->factored ) { set_err( "solve before a successful factor%s", "" ); return B200_ERR_STATE; }
+  if ( !holds_factor( c ) ) { set_err( "multi-GPU: the finished factor is collected on rank 0, which runs the sweeps (B200_REPLICATE_FACTOR=1 keeps a copy on every rank)%s", "" ); return B200_ERR_STATE; }
   if ( p <= 0 ) return B200_ERR_ARG;
   CK( cudaSetDevice( c->device ) );
   return run_solve( c, d_b, p, d_x );
@@ -1099,6 +1112,7 @@ extern "C" int b200_solve_device( b200_ctx_t* c, const double* d_b, int p, doubl
 
 extern "C" int b200_solve_host( b200_ctx_t* c, const double* b, int p, double* x ) {
   if ( !c || !c->factored ) { set_err( "solve before a successful factor%s", "" ); return B200_ERR_STATE; }
+  if ( !holds_factor( c ) ) { set_err( "multi-GPU: the finished factor is collected on rank 0, which runs the sweeps (B200_REPLICATE_FACTOR=1 keeps a copy on every rank)%s", "" ); return B200_ERR_STATE; }
   if ( p <= 0 || !b || !x ) return B200_ERR_ARG;
   CK( cudaSetDevice( c->device ) );
   if ( p > c->io_p_cap ) {
@@ -1167,6 +1181,7 @@ extern "C" int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t o
  * Deterministic (fixed reduction order), so equal factors give equal bits on any number of GPUs. */
 extern "C" int b200_factor_colnorms( b200_ctx_t* c, double* colsq ) {
   if ( !c || !colsq || !c->factored || c->dry ) return B200_ERR_STATE;
+  if ( !holds_factor( c ) ) { for ( int i = 0; i < c->n; i++ ) colsq[i] = 0.0; return B200_OK; }      /* only a rank with the whole factor reports it */
   CK( cudaSetDevice( c->device ) );
   double* d = nullptr; CK( cudaMalloc( &d, ( size_t )c->n * 8 ) );
   CK( cudaMemsetAsync( d, 0, ( size_t )c->n * 8, c->stream ) );

@@ -72,6 +72,33 @@ def convdiff27_full(nx, ny=None, nz=None, peh=0.5):
     return _coo_to_csc(n, np.concatenate(r), np.concatenate(c), np.concatenate(v))
 
 
+def convdiff7_central(nx, ny=None, nz=None, peh=8.0):
+    """3-D 7-point convection-diffusion with CENTRAL differences for the convection term: diag 6, neighbour in +direction
+    -1 + v*peh/2, in -direction -1 - v*peh/2 (velocity v = 1, 1/2, 1/4).  For peh > 2 the matrix is far from diagonally dominant
+    (off-diagonal row sum 6 + 1.75*peh against a diagonal of 6) and strongly unsymmetric: the LU pivoting test matrix."""
+    ny = ny or nx; nz = nz or nx
+    ids = _grid_ids((nz, ny, nx))
+    n = ids.size
+    r = [ids.ravel()]; c = [ids.ravel()]; v = [np.full(n, 6.0)]
+    for axis, vel in ((2, 1.0), (1, 0.5), (0, 0.25)):
+        lo = [slice(None)] * 3; hi = [slice(None)] * 3
+        lo[axis] = slice(0, -1); hi[axis] = slice(1, None)
+        a = ids[tuple(lo)].ravel(); b = ids[tuple(hi)].ravel()          # b is the +direction neighbour of a
+        r.append(a); c.append(b); v.append(np.full(a.size, -1.0 + 0.5 * vel * peh))
+        r.append(b); c.append(a); v.append(np.full(a.size, -1.0 - 0.5 * vel * peh))
+    return _coo_to_csc(n, np.concatenate(r), np.concatenate(c), np.concatenate(v))
+
+
+def random_weak_diagonal(n, density=0.01, diag=0.05, seed=0):
+    """random sparse unsymmetric matrix (values N(0,1)) whose diagonal is diag * N(0,1): nothing favours the diagonal as a pivot"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    A = sp.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csc")
+    A = (A + sp.diags(diag * rng.standard_normal(n))).tocsc()
+    A.sum_duplicates(); A.sort_indices()
+    return n, A.indptr.astype(np.uint32), A.indices.astype(np.uint32), A.data.astype(np.float64)
+
+
 def upper_to_full(n, colptr, rowidx, vals):
     cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(colptr.astype(np.int64)))
     rows = rowidx.astype(np.int64)

@@ -55,10 +55,16 @@ def test_replay_detects_a_broken_schedule(mc):
     mc.lib().b200_symbolic_free(S)
 
 
+@pytest.mark.parametrize("replicate", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_every_rank_ends_up_with_the_whole_factor(mc, world):
-    """the sweeps run replicated, so after the factorization every rank must hold every column of L and every 64x64 inverse
-    block: either it computed them (b200_plan_col_owner) or a message delivered them.  Checked from the exported messages."""
+def test_every_rank_ends_up_with_the_whole_factor(mc, world, replicate, monkeypatch):
+    """the sweeps run on rank 0 (default) or replicated (B200_REPLICATE_FACTOR=1), so after the factorization rank 0 / every rank must
+    hold every column of L and every 64x64 inverse block: either it computed them (b200_plan_col_owner) or a message delivered them.
+    Checked from the exported messages; without replication no other rank may receive bulk factor traffic it does not need."""
+    if replicate:
+        monkeypatch.setenv("B200_REPLICATE_FACTOR", "1")
+    else:
+        monkeypatch.delenv("B200_REPLICATE_FACTOR", raising=False)
     import numpy as np
     from helpers import sym_dict
     n, cp, ri, v = stencils.poisson3d_upper(22)
@@ -76,7 +82,7 @@ def test_every_rank_ends_up_with_the_whole_factor(mc, world):
     nblk = (k + 63) // 64; blk0 = np.concatenate([[0], np.cumsum(nblk)])
     invsz = (k // 64) * 4096 + (k % 64) ** 2; invp = np.concatenate([[0], np.cumsum(invsz)])
     assert np.array_equal(lp[1:] - lp[:-1], ld * k)
-    for r in range(world):
+    for r in (range(world) if replicate else [0]):
         have = np.zeros(n, dtype=bool); have_inv = np.zeros(blk0[-1], dtype=bool)
         for s in range(ns):
             for c in range(k[s]):

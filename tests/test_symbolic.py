@@ -32,9 +32,13 @@ def test_etree_colcounts_nnz_bit_exact(mc, name, gen, ordering):
     assert np.array_equal(d["colcount"], fac["colcount"])      # column counts, bit exact
     assert d["nnzL"] == fac["nnz"] == int(d["colcount"].sum())
     assert d["flops"] == float((d["colcount"].astype(np.float64) ** 2).sum())
-    # independent pin of the oracle itself: dense Cholesky of the permuted matrix
+    # independent pin of the oracle itself: dense Cholesky of the permuted matrix -- the column counts, and the elimination tree
+    # read off the factor by its definition  parent[j] = min { i > j : l_ij != 0 }  (no shared code with b200_etree / oracle_etree)
     A = stencils.to_scipy(n, cp, ri, v, True).toarray()
     assert np.array_equal(d["colcount"], dense_colcounts(A, perm))
+    Ld = np.abs(np.linalg.cholesky(A[np.ix_(perm, perm)])) > 0
+    dense_parent = np.array([next((i for i in range(j + 1, n) if Ld[i, j]), -1) for j in range(n)], dtype=np.int32)
+    assert np.array_equal(d["parent"], dense_parent)
     # postordered: every parent has a larger index than its children
     assert np.all((d["parent"] > np.arange(n)) | (d["parent"] == -1))
     mc.lib().b200_symbolic_free(S)
