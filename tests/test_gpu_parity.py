@@ -353,6 +353,63 @@ def test_lu_vs_oracle_and_backward_error(mc, name, gen):
     s.close()
 
 
+@pytest.mark.parametrize("dims,peh", [((24, 24, 24), 4.0), ((24, 24, 24), 64.0), ((40, 38, 36), 16.0)])
+def test_lu_threshold_pivoting_holds_on_matrices_that_are_not_diagonally_dominant(mc, dims, peh):
+    """central-difference convection at cell Peclet numbers >> 2: off-diagonal row sums several times the diagonal, strongly unsymmetric.
+    The factorization must satisfy threshold partial pivoting (u = 0.1, UMFPACK's default, src/solver_umfpack.c:98) over ALL fully-summed
+    rows of every front -- verified on the device from the finished multipliers -- with no perturbed pivot, and agree with SuperLU."""
+    import scipy.sparse.linalg as sla
+    n, cp, ri, v = stencils.convdiff7_central(*dims, peh=peh)
+    A = stencils.to_scipy(n, cp, ri, v)
+    off = np.asarray(np.abs(A - sp.diags(A.diagonal())).sum(axis=1)).ravel()
+    assert np.median(off) > 1.2 * 6.0                                                   # interior rows are not diagonally dominant
+    s = mc.Solver(); S = s.analyze(n, cp, ri, mc.KIND_LU)
+    assert np.diff(mc.sym_array(s.S, "sn_start", S.ns + 1, np.int32)).max() > 256       # fronts with several diagonal blocks
+    assert s.factor(v) == 0, s.err()
+    st = s.stats()
+    assert st.npiv_perturbed == 0 and st.npiv_threshold_violations == 0 and 1.0 <= st.lu_max_multiplier <= 1.0 / st.pivot_threshold
+    B = np.stack([np.arange(n, dtype=float), np.cos(np.arange(n))], axis=1)
+    X = s.solve(B)
+    for c in range(2):
+        assert backward_error(A, X[:, c], B[:, c]) <= 1e-12
+    Xs = sla.splu(A.tocsc()).solve(B)
+    assert np.abs(X - Xs).max() <= 1e-10 * np.abs(Xs).max()
+    s.close()
+
+
+def test_lu_weak_diagonal_is_flagged_never_silently_wrong(mc, tmp_path):
+    """random sparse matrix with a weak diagonal: pivots from outside the 64-row diagonal blocks (or delayed pivots) would be needed.
+    The backend must SAY so: multipliers beyond 1/u and perturbed pivots are counted, the shim reports the true backward error of the
+    refined solution, and the plugin / CLI abort like the reference's assert( status == UMFPACK_OK ) instead of printing garbage."""
+    n, cp, ri, v = stencils.random_weak_diagonal(1500, 0.004)
+    A = stencils.to_scipy(n, cp, ri, v)
+    s = mc.Solver(); s.analyze(n, cp, ri, mc.KIND_LU)
+    assert s.factor(v) == 0
+    st = s.stats()
+    b = np.arange(n, dtype=float)
+    try:
+        x = s.solve(b)
+        be = backward_error(A, x, b)
+        st2 = s.stats()
+        assert be <= 1e-10 or ((st.npiv_threshold_violations > 0 or st.npiv_perturbed > 0) and st2.backward_error > 1e-12)
+    except RuntimeError as e:                                   # non-finite solution: B200_ERR_SINGULAR
+        assert "not finite" in str(e)
+    s.close()
+    path = tmp_path / "weak.mm"
+    stencils.write_mm(str(path), n, cp, ri, v)
+    r = subprocess.run([mc.CLI_PATH, "-i", str(path), "-o", "-"], capture_output=True, text=True)
+    if st.npiv_perturbed > 0:
+        assert r.returncode != 0 and ("numerically singular" in r.stderr or "not finite" in r.stderr), (r.returncode, r.stderr[-300:])
+
+
+def test_nan_in_the_matrix_fails_the_factorization(mc):
+    n, cp, ri, v = stencils.convdiff27_full(6)
+    v = v.copy(); v[len(v) // 2] = np.nan
+    s = mc.Solver(); s.analyze(n, cp, ri, mc.KIND_LU)
+    assert s.factor(v) == mc.B200_ERR_SINGULAR and "NaN" in s.err()
+    s.close()
+
+
 def test_lu_needs_pivoting_inside_the_front(mc, golden):
     """tests/unsym.mm has zero diagonal entries: only row interchanges make it factorable"""
     Ad = read_mm_dense(f"{golden}/unsym.mm")
