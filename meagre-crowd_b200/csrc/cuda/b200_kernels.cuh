@@ -60,7 +60,8 @@ struct AsmTask { int parent; int col0; int ncols; };
 struct SnMeta {           /* per supernode, device copy */
   int64_t lptr, uptr, cbptr, rowptr, invptr;
   int c0, k, f, parent, depth, child_begin, child_end, ld;   /* ld: leading dimension of the panel (f rounded up to even) */
-  int64_t wptr;           /* solve workspace row offset within its level arena */
+  int64_t wptr;           /* solve workspace row offset within its level arena (tensor-path sweeps, p >= 5) */
+  int64_t wgl;            /* ... within the one-region-per-supernode workspace of the persistent sweeps (p <= 4) */
   int64_t sinv;           /* offset of its solve-block inverses: block t at sinv + t * sbw^2, leading dimension = width rounded up to even */
   int sbw;                /* solve block width: SB, or SB_WIDE for the big fronts */
 };

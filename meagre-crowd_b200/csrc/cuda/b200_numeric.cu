@@ -26,6 +26,7 @@
 #include <nccl.h>      /* types only: the library is bound at run time (the copy torch has already loaded, else the system one) */
 #include "solver_b200.h"
 #include "b200_kernels.cuh"
+#include "b200_sweep.cuh"
 
 using namespace b200;
 
@@ -95,7 +96,7 @@ struct Launch { int kind; int64_t first; int64_t count; int depth; double flops;
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
 
 /* solve schedule */
-enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_TRI, SK_FWD_UPD, SK_BWD_GATHER, SK_BWD_UPD, SK_BWD_TRI, SK_FWD_SMALL, SK_BWD_SMALL, SK_COUNT };
+enum SolveKind { SK_FWD_ZERO_W = 0, SK_FWD_GATHER, SK_FWD_TRI, SK_FWD_UPD, SK_BWD_GATHER, SK_BWD_UPD, SK_BWD_TRI, SK_FWD_SMALL, SK_BWD_SMALL, SK_SWEEP_FWD, SK_SWEEP_BWD, SK_COUNT };
 /* one launch of a sweep: gather / zero launches use first,count; product launches carry their tiles in the FMA list (t0,nt: 32 outputs per
  * tile for gemv-type tasks, 32 for gemvT-type) and in the tensor-path list (g0,ng: 64 outputs per tile) */
 struct SLaunch { int kind; int depth; int64_t first, count; int64_t t0, nt; int64_t g0, ng; };
@@ -145,6 +146,8 @@ struct b200_ctx {
   DevVec<SvTask> sv_tasks; DevVec<SvTile> sv_tiles_v, sv_tiles_t, sv_tiles_g; DevVec<GatherTask> bgather_tasks; DevVec<int> sv_small;
   SvGemm* dSvGemm = nullptr; int sv_gemm_p = 0; int solve_wide_min = SB_WIDE_MIN;
   std::vector<SLaunch> slaunches;
+  /* persistent sweeps (p <= 4): ordered unit lists with device-side dependencies, b200_sweep.cuh */
+  DevVec<SvUnit> sw_units_f, sw_units_b; DevVec<SvTask> sw_tasks; int64_t sw_w_rows = 0; int64_t sw_ncnt = 0; int* dSwCnt = nullptr; double* dWg = nullptr; bool use_sweep = true; int64_t sw_head = 0; int sw_occ[3] = { 0, 0, 0 }; int sw_err_h = 0; std::vector<SvUnit> h_sw_f, h_sw_b; std::vector<SvTask> h_sw_t;
   int64_t sinvsize = 0;
   DevVec<GatherTask> gather_tasks;
   double* dZ = nullptr;
@@ -200,6 +203,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_NT ) );
   CKN( cudaFuncSetAttribute( gemm_solve_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SVG_SMEM_BT ) );
   { const char* e = getenv( "B200_SOLVE_WIDE_MIN" ); if ( e ) c->solve_wide_min = std::max( 2 * SB, atoi( e ) ); }     /* test hook: wide solve blocks on small problems */
+  CKN( cudaFuncSetAttribute( sv_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw_smem<1>() ) ); CKN( cudaFuncSetAttribute( sv_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw_smem<2>() ) ); CKN( cudaFuncSetAttribute( sv_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw_smem<4>() ) );
+  CKN( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &c->sw_occ[0], sv_sweep_kernel<1>, SW_THREADS, sw_smem<1>() ) ); CKN( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &c->sw_occ[1], sv_sweep_kernel<2>, SW_THREADS, sw_smem<2>() ) ); CKN( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &c->sw_occ[2], sv_sweep_kernel<4>, SW_THREADS, sw_smem<4>() ) );
   memset( &c->stats, 0, sizeof( c->stats ) );
   return c;
 }
@@ -262,6 +267,7 @@ static void release_symbolic( b200_ctx* c ) {
   c->small_sns.release(); c->sv_tasks.release(); c->sv_tiles_v.release(); c->sv_tiles_t.release(); c->sv_tiles_g.release(); c->gather_tasks.release(); c->bgather_tasks.release(); c->sv_small.release();
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dSvGemm );
   c->dR = c->dD = c->dZ = nullptr; c->dSvGemm = nullptr; c->sv_gemm_p = 0;
+  c->sw_tasks.release(); c->sw_units_f.release(); c->sw_units_b.release(); cudaFree( c->dSwCnt ); cudaFree( c->dWg ); c->dSwCnt = nullptr; c->dWg = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
   c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
   c->factored = false; c->device_bytes = 0;
@@ -329,7 +335,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   { std::vector<int> w( child_cnt.begin(), child_cnt.end() - 1 ); for ( int s = 0; s < ns; s++ ) if ( S->sn_parent[s] >= 0 ) child_list[w[S->sn_parent[s]]++] = s; }
   std::vector<std::vector<int>> levels( S->maxdepth + 1 );
   c->level_cb.assign( S->maxdepth + 1, 0 ); c->level_w.assign( S->maxdepth + 1, 0 );
-  int64_t invoff = 0, sinvoff = 0;
+  int64_t invoff = 0, sinvoff = 0; c->sw_w_rows = 0;
   for ( int s = 0; s < ns; s++ ) {
     SnMeta& m = meta[s];
     m.lptr = S->lptr[s]; m.uptr = S->uptr[s]; m.cbptr = S->cbptr[s]; m.rowptr = S->rowptr[s];
@@ -343,6 +349,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     levels[d].push_back( s );
     c->level_cb[d] = std::max( c->level_cb[d], m.cbptr + ( ( u + 1 ) & ~( int64_t )1 ) * u );
     m.wptr = c->level_w[d]; c->level_w[d] += u;
+    m.wgl = c->sw_w_rows; c->sw_w_rows += u;
   }
   c->invsize = invoff; c->sinvsize = sinvoff;
   if ( c->world > 1 ) {
@@ -837,6 +844,123 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     if ( !c->dry && tk.size() ) CK( cudaMalloc( &c->dSvGemm, tk.size() * sizeof( SvGemm ) ) );
     c->sv_gemm_p = 0;
   }
+  /* ---- persistent sweeps for p <= 4 (b200_sweep.cuh): the products of the schedule above as ordered units with device-side
+   * dependencies.  Counters (one int each, zeroed before a forward sweep): per supernode KD children complete, GD gather units done,
+   * FT / BT triangular tiles done (forward / backward), FD / BN units done, BD backward complete; rt0[s] + tile: block updates applied
+   * to 32 pivot rows (then to 32 update rows) of s; ct0[s] + tile: products applied to 64 pivot columns of s in the backward sweep. */
+  {
+    std::vector<SvTask> tk; std::vector<SvUnit> uf, ub;
+    const bool use_small = getenv( "B200_NO_SMALL_SOLVE" ) == nullptr;
+    auto is_small = [&]( int s ) { return use_small && meta[s].k <= KC && meta[s].f <= 4 * SVS_THREADS; };
+    int64_t off = 0;
+    const int64_t KD = off; off += ns; const int64_t GD = off; off += ns; const int64_t FT = off; off += ns; const int64_t FD = off; off += ns;
+    const int64_t BD = off; off += ns; const int64_t BT = off; off += ns; const int64_t BN = off; off += ns;
+    std::vector<int64_t> rt0( ns ), ct0( ns );
+    for ( int s = 0; s < ns; s++ ) { const int k = meta[s].k, u = meta[s].f - meta[s].k; rt0[s] = off; off += ( k + 31 ) / 32 + ( u + 31 ) / 32; ct0[s] = off; off += ( k + 63 ) / 64; }
+    c->sw_head = off; off += 4;                      /* forward ticket, backward ticket, error flag */
+    c->sw_ncnt = off;
+    c->use_sweep = getenv( "B200_SOLVE_LEVELSET" ) == nullptr && off < ( int64_t )2000000000;
+    auto unit = [&]( int kind, int task, int o0, int aux, int sn ) { SvUnit u; memset( &u, 0, sizeof( u ) ); u.kind = kind; u.task = task; u.o0 = o0; u.aux = aux; u.sn = sn; u.w2 = -1; u.sig = -1; u.up = -1; return u; };
+    const double* Fb = c->dL; const double* Mb = TWO ? c->dU : c->dL;
+    std::vector<int> Tf( ns, 0 ), Tb( ns, 0 ), ngath( ns, 0 ), cum( ns, 0 );
+    if ( c->use_sweep ) {
+    for ( int d = S->maxdepth; d >= 0; d-- ) {
+      std::vector<int> bl;
+      for ( int s : levels[d] ) {
+        if ( !is_small( s ) ) { bl.push_back( s ); continue; }
+        SvUnit U = unit( UK_FWD_SMALL, 0, 0, 0, s ); const int nch = meta[s].child_end - meta[s].child_begin;
+        if ( nch > 0 ) { U.w2 = ( int )( KD + s ); U.v2 = nch; }
+        uf.push_back( U ); Tf[s]++;
+      }
+      for ( int s : bl ) {
+        const SnMeta& m = meta[s]; bool any = false;
+        for ( int ci = m.child_begin; ci < m.child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
+        if ( !any ) continue;
+        for ( int lo = 0; lo < m.f; lo += GATHER_ROWS ) {
+          SvUnit U = unit( UK_FWD_GATHER, 0, lo, std::min( m.f, lo + GATHER_ROWS ), s ); U.w2 = ( int )( KD + s ); U.v2 = m.child_end - m.child_begin; U.sig = ( int )( GD + s );
+          uf.push_back( U ); Tf[s]++; ngath[s]++;
+        }
+      }
+      int nblk = 0; for ( int s : bl ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      for ( int t = 0; t < nblk; t++ ) {
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          SvTask x; x.M = c->dSinvF + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 1; x.mode = 1;
+          x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0 + j0;
+          const int id = ( int )tk.size(); tk.push_back( x );
+          for ( int o0 = 0; o0 < nb; o0 += GV_ROWS ) {
+            SvUnit U = unit( UK_GEMV, id, o0, 0, s );
+            if ( t > 0 ) { U.w1 = ( int )( rt0[s] + j0 / 32 ); U.n1 = ( nb + 31 ) / 32; U.v1 = t; }
+            else if ( ngath[s] > 0 ) { U.w2 = ( int )( GD + s ); U.v2 = ngath[s]; }
+            U.sig = ( int )( FT + s ); uf.push_back( U ); Tf[s]++; cum[s]++;
+          } }
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 );
+          for ( int part = 0; part < 2; part++ ) {
+            SvTask x; x.ld = m.ld; x.K = nb; x.tri = 0; x.mode = 0; x.vsel = 1; x.voff = m.c0 + j0;
+            int tile0;
+            if ( part == 0 ) { x.M = Fb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.N = m.k - j0 - nb; x.dsel = 0; x.doff = m.c0 + j0 + nb; tile0 = ( j0 + nb ) / 32; }      /* pivot rows below the block */
+            else { x.M = Fb + m.lptr + m.k + ( int64_t )j0 * m.ld; x.N = m.f - m.k; x.dsel = 2; x.doff = m.wgl; tile0 = ( m.k + 31 ) / 32; }                                    /* update rows */
+            if ( x.N <= 0 ) continue;
+            const int id = ( int )tk.size(); tk.push_back( x );
+            for ( int o0 = 0; o0 < x.N; o0 += GV_ROWS ) {
+              SvUnit U = unit( UK_GEMV, id, o0, 0, s ); const int tile = tile0 + o0 / 32;
+              if ( t > 0 ) { U.w1 = ( int )( rt0[s] + tile ); U.n1 = 1; U.v1 = t; }
+              U.w2 = ( int )( FT + s ); U.v2 = cum[s]; U.sig = ( int )( rt0[s] + tile ); uf.push_back( U ); Tf[s]++;
+            }
+          } }
+      }
+    }
+    for ( SvUnit& U : uf ) { U.dn = ( int )( FD + U.sn ); U.dtot = Tf[U.sn]; U.up = meta[U.sn].parent >= 0 ? ( int )( KD + meta[U.sn].parent ) : -1; }
+    std::fill( cum.begin(), cum.end(), 0 );
+    for ( int d = 0; d <= S->maxdepth; d++ ) {
+      std::vector<int> bl;
+      for ( int s : levels[d] ) {
+        if ( !is_small( s ) ) { bl.push_back( s ); continue; }
+        SvUnit U = unit( UK_BWD_SMALL, 0, 0, 0, s );
+        if ( meta[s].parent >= 0 ) { U.w2 = ( int )( BD + meta[s].parent ); U.v2 = 1; }
+        ub.push_back( U ); Tb[s]++;
+      }
+      for ( int s : bl ) { const SnMeta& m = meta[s]; const int u = m.f - m.k; if ( u <= 0 ) continue;       /* z[pivots] -= M[update rows, :]' x[ancestors], x through the row list */
+        SvTask x; x.M = Mb + m.lptr + m.k; x.ld = m.ld; x.K = u; x.N = m.k; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = 0; x.dsel = 1; x.doff = m.c0;
+        const int id = ( int )tk.size(); tk.push_back( x );
+        for ( int o0 = 0; o0 < m.k; o0 += SW_GT_COLS ) {
+          SvUnit U = unit( UK_GEMVT, id, o0, 1, s );
+          if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = 1; }
+          U.sig = ( int )( ct0[s] + o0 / 64 ); ub.push_back( U ); Tb[s]++;
+        } }
+      int nblk = 0; for ( int s : bl ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
+      for ( int t = nblk - 1; t >= 0; t-- ) {
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 ); const int need = ( m.f > m.k ? 1 : 0 ) + ( ( m.k + m.sbw - 1 ) / m.sbw - 1 - t );
+          SvTask x; x.M = c->dSinvB + m.sinv + ( int64_t )t * m.sbw * m.sbw; x.ld = ( nb + 1 ) & ~1; x.K = nb; x.N = nb; x.tri = 2; x.mode = 1;
+          x.vsel = 1; x.voff = m.c0 + j0; x.dsel = 0; x.doff = m.c0 + j0;
+          const int id = ( int )tk.size(); tk.push_back( x );
+          for ( int o0 = 0; o0 < nb; o0 += GV_ROWS ) {
+            SvUnit U = unit( UK_GEMV, id, o0, 0, s );
+            if ( need > 0 ) { U.w1 = ( int )( ct0[s] + j0 / 64 ); U.n1 = ( nb + 63 ) / 64; U.v1 = need; }
+            else if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = 1; }
+            U.sig = ( int )( BT + s ); ub.push_back( U ); Tb[s]++; cum[s]++;
+          } }
+        if ( t == 0 ) break;
+        for ( int s : bl ) { const SnMeta& m = meta[s]; const int j0 = t * m.sbw; if ( j0 >= m.k ) continue;
+          const int nb = std::min( m.sbw, m.k - j0 ); const int need = ( m.f > m.k ? 1 : 0 ) + ( ( m.k + m.sbw - 1 ) / m.sbw - 1 - t );
+          SvTask x; x.M = Mb + m.lptr + j0; x.ld = m.ld; x.K = nb; x.N = j0; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0;
+          const int id = ( int )tk.size(); tk.push_back( x );
+          for ( int o0 = 0; o0 < j0; o0 += SW_GT_COLS ) {
+            SvUnit U = unit( UK_GEMVT, id, o0, 0, s ); const int tile = o0 / 64;
+            if ( need > 0 ) { U.w1 = ( int )( ct0[s] + tile ); U.n1 = 1; U.v1 = need; }
+            U.w2 = ( int )( BT + s ); U.v2 = cum[s]; U.sig = ( int )( ct0[s] + tile ); ub.push_back( U ); Tb[s]++;
+          } }
+      }
+    }
+    for ( SvUnit& U : ub ) { U.dn = ( int )( BN + U.sn ); U.dtot = Tb[U.sn]; U.up = ( int )( BD + U.sn ); }
+    }
+    if ( c->dry ) { c->h_sw_f = uf; c->h_sw_b = ub; c->h_sw_t = tk; }
+    if ( c->sw_tasks.upload( tk ) || c->sw_units_f.upload( uf ) || c->sw_units_b.upload( ub ) ) return B200_ERR_CUDA;
+    if ( !c->dry && c->use_sweep ) { CK( cudaMalloc( &c->dSwCnt, ( size_t )c->sw_ncnt * sizeof( int ) ) ); CK( cudaMalloc( &c->dWg, ( ( size_t )c->sw_w_rows + 2 ) * 4 * 8 ) ); }
+    c->device_bytes += c->sw_tasks.bytes() + c->sw_units_f.bytes() + c->sw_units_b.bytes() + c->sw_ncnt * 4 + ( c->sw_w_rows + 2 ) * 32;
+  }
   c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
                      c->asm_tasks.bytes() + c->sv_tasks.bytes() * 2 + c->sv_tiles_v.bytes() + c->sv_tiles_t.bytes() + c->sv_tiles_g.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
   return B200_OK;
@@ -982,8 +1106,42 @@ static int ensure_solve_ws( b200_ctx* c, int p ) {
   return B200_OK;
 }
 
+/* one pair of sweeps for p <= 4 as two persistent kernels (b200_sweep.cuh): units are taken from an ordered list and wait on the device
+ * for their inputs, so there is no launch per tree level / solve block and independent fronts overlap */
+template <int PCT>
+static int launch_sweep( b200_ctx* c, const SweepArgs& a, int occ, cudaStream_t st ) {
+  if ( a.nunits <= 0 ) return B200_OK;
+  const int grid = ( int )std::min<int64_t>( a.nunits, ( int64_t )c->prop.multiProcessorCount * std::max( occ, 1 ) );
+  sv_sweep_kernel<PCT><<<grid, SW_THREADS, sw_smem<PCT>(), st>>>( a );
+  return B200_OK;
+}
+static int sweep_persistent( b200_ctx* c, const double* d_b, int p, double* d_x, int64_t& nl ) {
+  cudaStream_t st = c->stream;
+  const int n = c->n, pitch = p;
+  const int pblocks = ( int )std::min<int64_t>( ( ( int64_t )n * pitch + 255 ) / 256, 148 * 32 );
+  permute_in_kernel<<<pblocks, 256, 0, st>>>( d_b, c->perm.d, n, p, pitch, c->dY );
+  CK( cudaMemsetAsync( c->dSwCnt, 0, ( size_t )( c->sw_head + 2 ) * sizeof( int ), st ) );      /* counters and the two tickets; the error flag behind them is cleared once per solve */
+  if ( c->sw_w_rows > 0 ) CK( cudaMemsetAsync( c->dWg, 0, ( size_t )c->sw_w_rows * pitch * 8, st ) );
+  SweepArgs a;
+  a.cnt = c->dSwCnt; a.err = c->dSwCnt + c->sw_head + 2; a.tasks = c->sw_tasks.d; a.sn = c->sn.d; a.child_list = c->child_list.d; a.relidx = c->relidx.d; a.rowidx = c->rowidx.d;
+  a.Lf = c->dL; a.Lb = c->kind == B200_KIND_CHOLESKY ? c->dL : c->dU; a.sinvF = c->dSinvF; a.sinvB = c->dSinvB;
+  a.B.b[0] = c->dY; a.B.b[1] = c->dZ; a.B.b[2] = c->dWg; a.B.b[3] = nullptr; a.p = p; a.pitch = pitch;
+  const int pi = p <= 1 ? 0 : p <= 2 ? 1 : 2;
+  for ( int dir = 0; dir < 2; dir++ ) {
+    a.units = dir == 0 ? c->sw_units_f.d : c->sw_units_b.d; a.nunits = ( int )( dir == 0 ? c->sw_units_f.n : c->sw_units_b.n ); a.head = c->dSwCnt + c->sw_head + dir;
+    if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
+    if ( pi == 0 ) launch_sweep<1>( c, a, c->sw_occ[0], st ); else if ( pi == 1 ) launch_sweep<2>( c, a, c->sw_occ[1], st ); else launch_sweep<4>( c, a, c->sw_occ[2], st );
+    if ( c->profile ) { CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) ); float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->sprof_ms[SK_SWEEP_FWD + dir] += ms; c->sprof_n[SK_SWEEP_FWD + dir]++; }
+  }
+  permute_out_kernel<<<pblocks, 256, 0, st>>>( c->dY, c->perm.d, n, p, pitch, d_x );
+  CK( cudaMemcpyAsync( &c->sw_err_h, c->dSwCnt + c->sw_head + 2, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  nl += 7;
+  return B200_OK;
+}
+
 /* one pair of sweeps: d_x = (LL')^-1 d_b  (or (LU)^-1), launches counted into nl */
 static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64_t& nl ) {
+  if ( p <= 4 && c->use_sweep ) return sweep_persistent( c, d_b, p, d_x, nl );
   cudaStream_t st = c->stream;
   const int n = c->n;
   const int pitch = solve_pitch( p );
@@ -1064,6 +1222,7 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
   int64_t nl = 0;
   for ( int k = 0; k < SK_COUNT; k++ ) { c->sprof_ms[k] = 0; c->sprof_n[k] = 0; }
   CK( cudaEventRecord( c->ev0, st ) );
+  if ( c->dSwCnt ) CK( cudaMemsetAsync( c->dSwCnt + c->sw_head + 2, 0, sizeof( int ), st ) );
   r = sweep_once( c, d_b, p, d_x, nl ); if ( r ) return r;
   /* iterative refinement with a double-double residual.  Automatic mode: the componentwise backward error
    * omega = max_i |r_i| / (|A||x|+|b|)_i is formed after every pair of sweeps; one correction step always when the
@@ -1096,6 +1255,7 @@ static int run_solve( b200_ctx* c, const double* d_b, int p, double* d_x ) {
   CK( cudaEventRecord( c->ev1, st ) );
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( st ) );
+  if ( c->sw_err_h != 0 ) { char a_[32]; snprintf( a_, 32, "%d", c->sw_err_h - 1 ); c->sw_err_h = 0; set_err( "persistent sweep: unit %s gave up waiting for its inputs (schedule error)%s", a_, "" ); return B200_ERR_CUDA; }
   float ms = 0; cudaEventElapsedTime( &ms, c->ev0, c->ev1 );
   c->stats.solve_ms = ms; c->stats.solve_launches = nl;
   return B200_OK;
@@ -1159,7 +1319,7 @@ extern "C" int b200_get_profile( b200_ctx_t* c, char* buf, size_t len ) {
   std::string s;
   char line[256];
   for ( int k = 0; k < LK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", kind_name[k], ( long long )c->prof_n[k], c->prof_ms[k] ); s += line; }
-  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_tri", "solve_fwd_upd", "solve_bwd_gather", "solve_bwd_upd", "solve_bwd_tri", "solve_fwd_small", "solve_bwd_small" };
+  static const char* sname[SK_COUNT] = { "solve_zero_w", "solve_fwd_gather", "solve_fwd_tri", "solve_fwd_upd", "solve_bwd_gather", "solve_bwd_upd", "solve_bwd_tri", "solve_fwd_small", "solve_bwd_small", "solve_sweep_fwd", "solve_sweep_bwd" };
   for ( int k = 0; k < SK_COUNT; k++ ) { snprintf( line, sizeof( line ), "%s launches=%lld ms=%.3f\n", sname[k], ( long long )c->sprof_n[k], c->sprof_ms[k] ); s += line; }
   { float t0 = 0; if ( !c->lvl_ev.empty() ) cudaEventElapsedTime( &t0, c->ev0, c->lvl_ev[0] ); snprintf( line, sizeof( line ), "levels_ms(deepest first; prologue %.2f):", t0 ); s += line;
     for ( float v : c->lvl_ms ) { snprintf( line, sizeof( line ), " %.2f", v ); s += line; } s += "\n"; }
@@ -1432,6 +1592,23 @@ extern "C" int64_t b200_debug_messages( b200_ctx_t* c, b200_msg_t* out, int64_t 
   for ( int64_t i = 0; i < n && i < cap; i++ ) { const Msg& m = c->msgs[i]; out[i].src = m.src; out[i].dst = m.dst; out[i].which = m.which; out[i].offset = m.off; out[i].count = m.cnt; }
   return n;
 }
+/* ---- export of the persistent-sweep unit lists (schedule-only contexts; tests/sweep_sim.py replays them on the CPU).
+ * dir: 0 forward, 1 backward; every unit is 16 ints (SvUnit).  Tasks: 8 int64 each = vsel, voff, K, dsel, doff, N, tri, mode. */
+extern "C" int64_t b200_debug_sweep_units( b200_ctx_t* c, int dir, int* out, int64_t cap ) {
+  if ( !c || !c->dry ) return -1;
+  const std::vector<SvUnit>& u = dir == 0 ? c->h_sw_f : c->h_sw_b;
+  const int64_t n = ( int64_t )u.size();
+  if ( out ) for ( int64_t i = 0; i < n && i < cap; i++ ) memcpy( out + 16 * i, &u[i], 64 );
+  return n;
+}
+extern "C" int64_t b200_debug_sweep_tasks( b200_ctx_t* c, int64_t* out, int64_t cap ) {
+  if ( !c || !c->dry ) return -1;
+  const int64_t n = ( int64_t )c->h_sw_t.size();
+  if ( out ) for ( int64_t i = 0; i < n && i < cap; i++ ) { const SvTask& t = c->h_sw_t[i]; int64_t* o = out + 8 * i;
+    o[0] = t.vsel; o[1] = t.voff; o[2] = t.K; o[3] = t.dsel; o[4] = t.doff; o[5] = t.N; o[6] = t.tri; o[7] = t.mode; }
+  return n;
+}
+extern "C" int64_t b200_debug_sweep_counters( b200_ctx_t* c ) { return c ? c->sw_ncnt : -1; }
 extern "C" const char* b200_debug_kind_name( int kind ) { return kind >= 0 && kind < LK_COUNT ? kind_name[kind] : "?"; }
 
 /* every memory range a compute launch of the factor schedule may read or write, as conservative intervals of doubles inside
