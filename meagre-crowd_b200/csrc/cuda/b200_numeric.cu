@@ -488,7 +488,41 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     }
     for ( int J = 0; J < maxk; J += NBO ) {
       const size_t panel_first = LS.size();
-      int ev_fwd_last = -1;                 /* last per-block panel piece I received as the owner of the next panel */
+      int ev_ring_last = -1;                /* record event of the last ring step in which a piece of this panel reached me */
+      /* A factored panel travels round its group as a RING, 64-column block by block: the owner hands block b to the owner of the
+       * next panel at step b (right after the block's row update, while the rest of the panel is still being factored), that rank
+       * hands it on at step b+1, and so on -- hop h carries block (step - h).  Every rank sends a panel once; the owner of panel
+       * J+h is hop h of the ring, so the ranks receive it in the order in which they need it.  (Round 1 sent the whole panel from its
+       * owner to every member: 7 x 77 MB out of one GPU per root panel at 8 GPUs, the largest item of the critical path.)
+       * The ring always closes over the whole group. */
+      auto ring_step = [&]( int sg, int Jp, bool after_compute ) {
+        const int64_t m0 = ( int64_t )MS.size(); bool i_recv = false, i_send_own = false;
+        for ( int s : lv ) {
+          const SnMeta& m = meta[s];
+          if ( !is_dist( s ) || Jp >= m.k ) continue;
+          const int gf = pl->grp_first[s], gs = pl->grp_size[s];
+          const int root = b200_plan_col_owner( pl, S, s, Jp );
+          const int nbp = ( std::min( NBO, m.k - Jp ) + NB - 1 ) / NB;                 /* blocks of this panel */
+          const int hops = gs - 1;                                                      /* every member ends up with every panel of the front (the collection of the finished factor relies on it) */
+          for ( int h = 0; h < hops; h++ ) {
+            const int b = sg - h; if ( b < 0 || b >= nbp ) continue;
+            const int src = gf + ( root - gf + h ) % gs, dst = gf + ( root - gf + h + 1 ) % gs;
+            if ( me != src && me != dst ) continue;
+            const int jb = Jp + b * NB, nb = std::min( NB, m.k - jb );
+            MS.push_back( { src, dst, 0, m.lptr + ( int64_t )jb * m.ld, ( int64_t )nb * m.ld } );
+            MS.push_back( { src, dst, 1, m.invptr + ( int64_t )( jb / NB ) * NB * NB, ( int64_t )nb * nb } );
+            c->comm_bytes += ( double )nb * m.ld * 8.0;
+            if ( me == dst ) i_recv = true;
+            if ( me == src && h == 0 ) i_send_own = true;
+          }
+        }
+        if ( ( int64_t )MS.size() == m0 ) return;
+        int wait = -1;
+        if ( i_send_own && after_compute ) { wait = new_event(); LS.back().record_ev = wait; }     /* LS.back(): my last compute launch of this block (row update, or the diagonal block) */
+        Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = wait; l.record_ev = new_event();
+        LS.push_back( l );
+        if ( i_recv ) ev_ring_last = l.record_ev;
+      };
       for ( int j0 = J; j0 < std::min( maxk, J + NBO ); j0 += NB ) {
         if ( j0 > J ) { /* left-looking inside the outer panel: the 64 columns about to be factored receive the update of ALL earlier
                          * blocks of the panel in one product (K = j0 - J) -- one read-modify-write of 64 columns instead of one
@@ -584,28 +618,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         if ( !tbt.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt.size(), d, tflops } ); tb.insert( tb.end(), tbt.begin(), tbt.end() ); }
         if ( !ttl2.empty() ) { LS.push_back( { LK_TRSM, ( int64_t )ttl.size(), ( int64_t )ttl2.size(), d, 0.0 } ); ttl.insert( ttl.end(), ttl2.begin(), ttl2.end() ); }
         if ( !tbt2.empty() ) { LS.push_back( { LK_TRSM_MMA, ( int64_t )tb.size(), ( int64_t )tbt2.size(), d, 0.0 } ); tb.insert( tb.end(), tbt2.begin(), tbt2.end() ); }
-        if ( any_dist ) { /* the 64 columns just finished go straight to the owner of the NEXT panel, while the rest of this panel is
-                           * still being factored: only the last block's transfer stays on the critical path */
-          const int64_t m0 = ( int64_t )MS.size(); bool i_recv = false, i_send = false;
-          for ( int s : lv ) {
-            const SnMeta& m = meta[s];
-            if ( !is_dist( s ) || j0 >= m.k ) continue;
-            const int root = b200_plan_col_owner( pl, S, s, J ), nxt = J + NBO < m.k ? b200_plan_col_owner( pl, S, s, J + NBO ) : -1;
-            if ( nxt < 0 || nxt == root || ( me != root && me != nxt ) ) continue;
-            const int nb = std::min( NB, m.k - j0 );
-            MS.push_back( { root, nxt, 0, m.lptr + ( int64_t )j0 * m.ld, ( int64_t )nb * m.ld } );
-            MS.push_back( { root, nxt, 1, m.invptr + ( int64_t )( j0 / NB ) * NB * NB, ( int64_t )nb * nb } );
-            c->comm_bytes += ( double )nb * m.ld * 8.0;
-            if ( me == nxt ) i_recv = true; else i_send = true;
-          }
-          if ( ( int64_t )MS.size() > m0 ) {
-            int wait = -1;
-            if ( i_send ) { wait = new_event(); LS.back().record_ev = wait; }     /* LS.back(): my last compute launch of this block (row update, or the diagonal block) */
-            Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = wait; l.record_ev = new_event();
-            LS.push_back( l );
-            if ( i_recv ) ev_fwd_last = l.record_ev;
-          }
-        }
+        if ( any_dist ) ring_step( ( j0 - J ) / NB, J, true );
         if ( !have_diag ) continue;
       }
       int ev_panel = -1;
@@ -618,32 +631,12 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           ev_panel = LS[ql].record_ev;
         }
       }
-      if ( any_dist ) { /* the factored panels (and their diagonal-block inverses) go from their owner to the rest of the group:
-                         * first to the owner of the NEXT panel -- the only copy the critical path waits for -- then to the others.
-                         * The owner itself goes on as soon as its panel is done (its sends only read the panel). */
-        const int ev_pdone = ev_panel;
-        if ( ev_fwd_last >= 0 ) ev_panel = ev_fwd_last;       /* I own the next panel: I have it all once the last block has arrived */
-        {
-          const int64_t m0 = ( int64_t )MS.size();
-          bool i_receive = false;
-          for ( int s : lv ) {
-            const SnMeta& m = meta[s];
-            if ( !is_dist( s ) || J >= m.k ) continue;
-            const int root = b200_plan_col_owner( pl, S, s, J ); const int kb = std::min( NBO, m.k - J );
-            const int nxt = J + NBO < m.k ? b200_plan_col_owner( pl, S, s, J + NBO ) : -1;
-            for ( int r = pl->grp_first[s]; r < pl->grp_first[s] + pl->grp_size[s]; r++ ) {
-              if ( r == root || r == nxt || ( me != root && me != r ) ) continue;
-              MS.push_back( { root, r, 0, m.lptr + ( int64_t )J * m.ld, ( int64_t )kb * m.ld } );
-              MS.push_back( { root, r, 1, m.invptr + ( int64_t )( J / NB ) * NB * NB, ( int64_t )( kb / NB ) * NB * NB + ( int64_t )( kb % NB ) * ( kb % NB ) } );
-              c->comm_bytes += ( double )kb * m.ld * 8.0;
-              if ( me == r ) i_receive = true;
-            }
-          }
-          if ( ( int64_t )MS.size() > m0 ) {
-            Launch l = { LK_BCAST, m0, ( int64_t )MS.size() - m0, d, 0.0 }; l.stream = 2; l.wait_ev = ev_pdone; l.record_ev = c->nevents++;
-            LS.push_back( l );
-            if ( i_receive ) ev_panel = l.record_ev;
-          }
+      if ( any_dist ) { /* the steps of the ring that are still due once the panel's last block has been factored */
+        const int nsteps_done = ( std::min( maxk, J + NBO ) - J + NB - 1 ) / NB;
+        for ( int sg = nsteps_done; sg < NBO / NB + c->world - 2; sg++ ) ring_step( sg, J, false );
+        if ( ev_ring_last >= 0 ) { /* a panel I did not factor is complete here once its last block has arrived; the update stream must wait for that AND for
+                                    * my own panels of this step (other fronts of the level): join the NCCL stream into the panel stream */
+          push_nop( d, 1 ); LS.back().wait_ev = ev_ring_last; LS.back().record_ev = new_event(); ev_panel = LS.back().record_ev;
         }
       }
       /* trailing update with the whole outer panel, in two launches: first the columns of the NEXT
