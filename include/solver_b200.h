@@ -224,11 +224,14 @@ const char* b200_debug_kind_name( int kind );
 typedef struct b200_access { int launch, which, write; int64_t offset, count; } b200_access_t;   /* conservative interval a compute launch reads (0) or writes (1) */
 int64_t b200_debug_accesses( b200_ctx_t* c, b200_access_t* out, int64_t cap );
 /* the ordered unit lists of the persistent sweeps (p <= 4; csrc/cuda/b200_sweep.cuh), schedule-only contexts: dir 0 forward / 1 backward,
- * 16 ints per unit (kind, task, o0, aux, sn, w1, n1, v1, w2, v2, sig, dn, dtot, up, 0, 0); tasks: 8 int64 each (vsel, voff, K, dsel, doff,
+ * 16 ints per unit (kind, task, o0, aux, sn, w1, n1, v1, w2, v2, sig, up, 0, 0, 0, 0); tasks: 8 int64 each (vsel, voff, K, dsel, doff,
  * N, tri, mode); number of dependency counters.  tests/sweep_sim.py replays them on the CPU (deadlock freedom, data races). */
 int64_t b200_debug_sweep_units( b200_ctx_t* c, int dir, int* out, int64_t cap );
 int64_t b200_debug_sweep_tasks( b200_ctx_t* c, int64_t* out, int64_t cap );
 int64_t b200_debug_sweep_counters( b200_ctx_t* c );
+/* per-unit time stamps of the last persistent sweep (context created with B200_SWEEP_TRACE set): 5 uint64 per unit (globaltimer ns at the
+ * start, clock64 at start / inputs ready / done, SM id) and the device unit list (16 ints per unit; small supernodes in batches of 8) */
+int64_t b200_debug_sweep_trace( b200_ctx_t* c, int dir, unsigned long long* trace, int* units, int64_t cap );
 
 /* checksum of the factor: colsq[j] = sum_i L(i,j)^2 over the stored rows of column j (permuted numbering), n doubles on the host;
  * fixed reduction order, so identical factors give identical bits (Cholesky: the total equals trace(A)) */

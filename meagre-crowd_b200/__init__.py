@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
     "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dgemm_variant", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
     "b200_outer_width", "b200_set_outer_width_cap", "b200_plan_create", "b200_plan_free", "b200_plan_col_owner", "b200_plan_member", "b200_plan_cb_transfers",
-    "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank", "b200_bench_potrf_us", "b200_bench_dgemm_bulk_variant", "b200_ctx_create_dry", "b200_debug_schedule", "b200_debug_messages", "b200_debug_kind_name", "b200_debug_accesses", "b200_factor_colnorms", "b200_debug_sweep_units", "b200_debug_sweep_tasks", "b200_debug_sweep_counters",
+    "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank", "b200_bench_potrf_us", "b200_bench_dgemm_bulk_variant", "b200_ctx_create_dry", "b200_debug_schedule", "b200_debug_messages", "b200_debug_kind_name", "b200_debug_accesses", "b200_factor_colnorms", "b200_debug_sweep_units", "b200_debug_sweep_tasks", "b200_debug_sweep_counters", "b200_debug_sweep_trace",
 ]
 
 _lib = None
@@ -174,6 +174,7 @@ def lib():
     L.b200_debug_sweep_units.restype = i64; L.b200_debug_sweep_units.argtypes = [vp, C.c_int, vp, i64]
     L.b200_debug_sweep_tasks.restype = i64; L.b200_debug_sweep_tasks.argtypes = [vp, vp, i64]
     L.b200_debug_sweep_counters.restype = i64; L.b200_debug_sweep_counters.argtypes = [vp]
+    L.b200_debug_sweep_trace.restype = i64; L.b200_debug_sweep_trace.argtypes = [vp, C.c_int, vp, vp, i64]
     L.b200_debug_kind_name.restype = C.c_char_p; L.b200_debug_kind_name.argtypes = [i32]
     L.b200_ctx_create.restype = vp; L.b200_ctx_create.argtypes = [i32]
     L.b200_ctx_destroy.argtypes = [vp]

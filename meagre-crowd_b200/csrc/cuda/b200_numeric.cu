@@ -147,7 +147,7 @@ struct b200_ctx {
   SvGemm* dSvGemm = nullptr; int sv_gemm_p = 0; int solve_wide_min = SB_WIDE_MIN;
   std::vector<SLaunch> slaunches;
   /* persistent sweeps (p <= 4): ordered unit lists with device-side dependencies, b200_sweep.cuh */
-  DevVec<SvUnit> sw_units_f, sw_units_b; DevVec<SvTask> sw_tasks; int64_t sw_w_rows = 0; int64_t sw_ncnt = 0; int* dSwCnt = nullptr; double* dWg = nullptr; bool use_sweep = true; int64_t sw_head = 0; int sw_occ[3] = { 0, 0, 0 }; int sw_err_h = 0; std::vector<SvUnit> h_sw_f, h_sw_b; std::vector<SvTask> h_sw_t;
+  DevVec<SvUnit> sw_units[2]; /* forward, backward */ DevVec<SvTask> sw_tasks; DevVec<SvUnit> sw_inner; int64_t sw_w_rows = 0; int64_t sw_ncnt = 0; int* dSwCnt = nullptr; double* dWg = nullptr; unsigned long long* dSwTrace = nullptr; bool use_sweep = true; int sweep_pmax = 1;      /* measured on 128^3: 14.0 ms against 14.4 (level-set launches) at p = 1, but 17.4 / 27 against 14.5 / 20.4 at p = 2 / 4 -- B200_SWEEP_PMAX widens it for the tests */ int64_t sw_head = 0; int sw_occ[3] = { 0, 0, 0 }; int sw_err_h = 0; std::vector<SvUnit> h_sw_f, h_sw_b; std::vector<SvTask> h_sw_t;
   int64_t sinvsize = 0;
   DevVec<GatherTask> gather_tasks;
   double* dZ = nullptr;
@@ -196,6 +196,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM ) );
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
   c->replicate = getenv( "B200_REPLICATE_FACTOR" ) != nullptr;
+  { const char* e = getenv( "B200_SWEEP_PMAX" ); if ( e ) c->sweep_pmax = std::max( 0, std::min( 4, atoi( e ) ) ); }
   CKN( cudaFuncSetAttribute( trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM ) );
   CKN( cudaFuncSetAttribute( build_sinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SINV_SMEM ) );
   CKN( cudaFuncSetAttribute( sv_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_gemv_smem<4>() ) );
@@ -267,7 +268,7 @@ static void release_symbolic( b200_ctx* c ) {
   c->small_sns.release(); c->sv_tasks.release(); c->sv_tiles_v.release(); c->sv_tiles_t.release(); c->sv_tiles_g.release(); c->gather_tasks.release(); c->bgather_tasks.release(); c->sv_small.release();
   cudaFree( c->dY ); cudaFree( c->dW[0] ); cudaFree( c->dW[1] ); cudaFree( c->dB ); cudaFree( c->dX ); cudaFree( c->dR ); cudaFree( c->dD ); cudaFree( c->dZ ); cudaFree( c->dSvGemm );
   c->dR = c->dD = c->dZ = nullptr; c->dSvGemm = nullptr; c->sv_gemm_p = 0;
-  c->sw_tasks.release(); c->sw_units_f.release(); c->sw_units_b.release(); cudaFree( c->dSwCnt ); cudaFree( c->dWg ); c->dSwCnt = nullptr; c->dWg = nullptr;
+  c->sw_tasks.release(); for ( int i = 0; i < 2; i++ ) c->sw_units[i].release(); c->sw_inner.release(); cudaFree( c->dSwCnt ); cudaFree( c->dWg ); cudaFree( c->dSwTrace ); c->dSwCnt = nullptr; c->dWg = nullptr; c->dSwTrace = nullptr;
   c->dY = c->dW[0] = c->dW[1] = c->dB = c->dX = nullptr; c->solve_p_cap = 0; c->io_p_cap = 0;
   c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
   c->factored = false; c->device_bytes = 0;
@@ -837,17 +838,17 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     if ( !c->dry && tk.size() ) CK( cudaMalloc( &c->dSvGemm, tk.size() * sizeof( SvGemm ) ) );
     c->sv_gemm_p = 0;
   }
-  /* ---- persistent sweeps for p <= 4 (b200_sweep.cuh): the products of the schedule above as ordered units with device-side
-   * dependencies.  Counters (one int each, zeroed before a forward sweep): per supernode KD children complete, GD gather units done,
-   * FT / BT triangular tiles done (forward / backward), FD / BN units done, BD backward complete; rt0[s] + tile: block updates applied
-   * to 32 pivot rows (then to 32 update rows) of s; ct0[s] + tile: products applied to 64 pivot columns of s in the backward sweep. */
+  /* ---- persistent sweeps (b200_sweep.cuh): the products of the schedule above as ordered units with device-side dependencies.
+   * Counters (one int each, zeroed before a forward sweep): per supernode KD units of its children done, GD gather units done, FT / BT
+   * triangular-product tiles done (forward / backward), BD its units done in the backward sweep; rt0[s] + tile: block updates applied to 32
+   * pivot rows (then to 32 update rows) of s; ct0[s] + tile: products applied to 64 pivot columns of s in the backward sweep. */
   {
     std::vector<SvTask> tk; std::vector<SvUnit> uf, ub;
     const bool use_small = getenv( "B200_NO_SMALL_SOLVE" ) == nullptr;
     auto is_small = [&]( int s ) { return use_small && meta[s].k <= KC && meta[s].f <= 4 * SVS_THREADS; };
     int64_t off = 0;
-    const int64_t KD = off; off += ns; const int64_t GD = off; off += ns; const int64_t FT = off; off += ns; const int64_t FD = off; off += ns;
-    const int64_t BD = off; off += ns; const int64_t BT = off; off += ns; const int64_t BN = off; off += ns;
+    const int64_t KD = off; off += ns; const int64_t GD = off; off += ns; const int64_t FT = off; off += ns;
+    const int64_t BD = off; off += ns; const int64_t BT = off; off += ns;
     std::vector<int64_t> rt0( ns ), ct0( ns );
     for ( int s = 0; s < ns; s++ ) { const int k = meta[s].k, u = meta[s].f - meta[s].k; rt0[s] = off; off += ( k + 31 ) / 32 + ( u + 31 ) / 32; ct0[s] = off; off += ( k + 63 ) / 64; }
     c->sw_head = off; off += 4;                      /* forward ticket, backward ticket, error flag */
@@ -862,7 +863,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
       for ( int s : levels[d] ) {
         if ( !is_small( s ) ) { bl.push_back( s ); continue; }
         SvUnit U = unit( UK_FWD_SMALL, 0, 0, 0, s ); const int nch = meta[s].child_end - meta[s].child_begin;
-        if ( nch > 0 ) { U.w2 = ( int )( KD + s ); U.v2 = nch; }
+        if ( nch > 0 ) { U.w2 = ( int )( KD + s ); U.v2 = -1; }      /* value filled in below: the units of all its children */
         uf.push_back( U ); Tf[s]++;
       }
       for ( int s : bl ) {
@@ -870,7 +871,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         for ( int ci = m.child_begin; ci < m.child_end; ci++ ) { const SnMeta& ch = meta[child_list[ci]]; if ( ch.f > ch.k ) { any = true; break; } }
         if ( !any ) continue;
         for ( int lo = 0; lo < m.f; lo += GATHER_ROWS ) {
-          SvUnit U = unit( UK_FWD_GATHER, 0, lo, std::min( m.f, lo + GATHER_ROWS ), s ); U.w2 = ( int )( KD + s ); U.v2 = m.child_end - m.child_begin; U.sig = ( int )( GD + s );
+          SvUnit U = unit( UK_FWD_GATHER, 0, lo, std::min( m.f, lo + GATHER_ROWS ), s ); U.w2 = ( int )( KD + s ); U.v2 = -1; U.sig = ( int )( GD + s );
           uf.push_back( U ); Tf[s]++; ngath[s]++;
         }
       }
@@ -892,7 +893,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           for ( int part = 0; part < 2; part++ ) {
             SvTask x; x.ld = m.ld; x.K = nb; x.tri = 0; x.mode = 0; x.vsel = 1; x.voff = m.c0 + j0;
             int tile0;
-            if ( part == 0 ) { x.M = Fb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.N = m.k - j0 - nb; x.dsel = 0; x.doff = m.c0 + j0 + nb; tile0 = ( j0 + nb ) / 32; }      /* pivot rows below the block */
+            if ( part == 0 ) { x.M = Fb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld; x.N = m.k - j0 - nb; x.dsel = 0; x.doff = m.c0 + j0 + nb; tile0 = ( j0 + nb ) / 32; }      /* pivot rows below the block (the next block's rows first) */
             else { x.M = Fb + m.lptr + m.k + ( int64_t )j0 * m.ld; x.N = m.f - m.k; x.dsel = 2; x.doff = m.wgl; tile0 = ( m.k + 31 ) / 32; }                                    /* update rows */
             if ( x.N <= 0 ) continue;
             const int id = ( int )tk.size(); tk.push_back( x );
@@ -904,22 +905,26 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           } }
       }
     }
-    for ( SvUnit& U : uf ) { U.dn = ( int )( FD + U.sn ); U.dtot = Tf[U.sn]; U.up = meta[U.sn].parent >= 0 ? ( int )( KD + meta[U.sn].parent ) : -1; }
+    { /* completion: every unit of s raises its parent's KD counter; the parent's first units wait for the units of ALL its children */
+      std::vector<int> kids( ns, 0 );
+      for ( int s = 0; s < ns; s++ ) if ( meta[s].parent >= 0 ) kids[meta[s].parent] += Tf[s];
+      for ( SvUnit& U : uf ) { U.up = meta[U.sn].parent >= 0 ? ( int )( KD + meta[U.sn].parent ) : -1; if ( U.w2 == ( int )( KD + U.sn ) ) U.v2 = kids[U.sn]; }
+    }
     std::fill( cum.begin(), cum.end(), 0 );
     for ( int d = 0; d <= S->maxdepth; d++ ) {
       std::vector<int> bl;
       for ( int s : levels[d] ) {
         if ( !is_small( s ) ) { bl.push_back( s ); continue; }
         SvUnit U = unit( UK_BWD_SMALL, 0, 0, 0, s );
-        if ( meta[s].parent >= 0 ) { U.w2 = ( int )( BD + meta[s].parent ); U.v2 = 1; }
+        if ( meta[s].parent >= 0 ) { U.w2 = ( int )( BD + meta[s].parent ); U.v2 = -1; }
         ub.push_back( U ); Tb[s]++;
       }
       for ( int s : bl ) { const SnMeta& m = meta[s]; const int u = m.f - m.k; if ( u <= 0 ) continue;       /* z[pivots] -= M[update rows, :]' x[ancestors], x through the row list */
         SvTask x; x.M = Mb + m.lptr + m.k; x.ld = m.ld; x.K = u; x.N = m.k; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = 0; x.dsel = 1; x.doff = m.c0;
         const int id = ( int )tk.size(); tk.push_back( x );
-        for ( int o0 = 0; o0 < m.k; o0 += SW_GT_COLS ) {
+        for ( int o0 = ( ( m.k - 1 ) / SW_GT_COLS ) * SW_GT_COLS; o0 >= 0; o0 -= SW_GT_COLS ) {      /* the last columns first: the first triangular product waits for them */
           SvUnit U = unit( UK_GEMVT, id, o0, 1, s );
-          if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = 1; }
+          if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = -1; }
           U.sig = ( int )( ct0[s] + o0 / 64 ); ub.push_back( U ); Tb[s]++;
         } }
       int nblk = 0; for ( int s : bl ) nblk = std::max( nblk, ( meta[s].k + meta[s].sbw - 1 ) / meta[s].sbw );
@@ -932,7 +937,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           for ( int o0 = 0; o0 < nb; o0 += GV_ROWS ) {
             SvUnit U = unit( UK_GEMV, id, o0, 0, s );
             if ( need > 0 ) { U.w1 = ( int )( ct0[s] + j0 / 64 ); U.n1 = ( nb + 63 ) / 64; U.v1 = need; }
-            else if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = 1; }
+            else if ( m.parent >= 0 ) { U.w2 = ( int )( BD + m.parent ); U.v2 = -1; }
             U.sig = ( int )( BT + s ); ub.push_back( U ); Tb[s]++; cum[s]++;
           } }
         if ( t == 0 ) break;
@@ -940,19 +945,35 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           const int nb = std::min( m.sbw, m.k - j0 ); const int need = ( m.f > m.k ? 1 : 0 ) + ( ( m.k + m.sbw - 1 ) / m.sbw - 1 - t );
           SvTask x; x.M = Mb + m.lptr + j0; x.ld = m.ld; x.K = nb; x.N = j0; x.tri = 0; x.mode = 0; x.vsel = 0; x.voff = m.c0 + j0; x.dsel = 1; x.doff = m.c0;
           const int id = ( int )tk.size(); tk.push_back( x );
-          for ( int o0 = 0; o0 < j0; o0 += SW_GT_COLS ) {
+          for ( int o0 = j0 - SW_GT_COLS; o0 >= 0; o0 -= SW_GT_COLS ) {      /* the previous block's columns first */
             SvUnit U = unit( UK_GEMVT, id, o0, 0, s ); const int tile = o0 / 64;
             if ( need > 0 ) { U.w1 = ( int )( ct0[s] + tile ); U.n1 = 1; U.v1 = need; }
             U.w2 = ( int )( BT + s ); U.v2 = cum[s]; U.sig = ( int )( ct0[s] + tile ); ub.push_back( U ); Tb[s]++;
           } }
       }
     }
-    for ( SvUnit& U : ub ) { U.dn = ( int )( BN + U.sn ); U.dtot = Tb[U.sn]; U.up = ( int )( BD + U.sn ); }
+    for ( SvUnit& U : ub ) { U.up = ( int )( BD + U.sn ); if ( meta[U.sn].parent >= 0 && U.w2 == ( int )( BD + meta[U.sn].parent ) ) U.v2 = Tb[meta[U.sn].parent]; }      /* x of all ancestors is final once every unit of the parent is done */
     }
-    if ( c->dry ) { c->h_sw_f = uf; c->h_sw_b = ub; c->h_sw_t = tk; }
-    if ( c->sw_tasks.upload( tk ) || c->sw_units_f.upload( uf ) || c->sw_units_b.upload( ub ) ) return B200_ERR_CUDA;
+    if ( c->dry ) { c->h_sw_f = uf; c->h_sw_b = ub; c->h_sw_t = tk; }      /* exported one unit per tile / supernode: that is what tests/sweep_sim.py checks */
+    /* device lists: runs of latency-bound units (small supernodes, gemv tiles with K <= SW_WARP_K) become UK_BATCH units of up to SW_BATCH,
+     * one inner unit per warp (waits and signals stay per inner unit) */
+    std::vector<SvUnit> inner;
+    auto warp_unit = [&]( const SvUnit& U ) { return U.kind == UK_FWD_SMALL || U.kind == UK_BWD_SMALL || ( U.kind == UK_GEMV && tk[U.task].K <= SW_WARP_K ); };
+    auto pack = [&]( std::vector<SvUnit>& in ) {
+      std::vector<SvUnit> out; out.reserve( in.size() / 4 + 16 );
+      for ( size_t i = 0; i < in.size(); ) {
+        if ( !warp_unit( in[i] ) ) { out.push_back( in[i++] ); continue; }
+        SvUnit B = unit( UK_BATCH, ( int )inner.size(), 0, 0, in[i].sn );
+        while ( i < in.size() && warp_unit( in[i] ) && B.o0 < SW_BATCH ) { inner.push_back( in[i] ); B.o0++; i++; }
+        out.push_back( B );
+      }
+      in.swap( out );
+    };
+    pack( uf ); pack( ub );
+    if ( c->sw_tasks.upload( tk ) || c->sw_inner.upload( inner ) || c->sw_units[0].upload( uf ) || c->sw_units[1].upload( ub ) ) return B200_ERR_CUDA;
+    if ( !c->dry && c->use_sweep && getenv( "B200_SWEEP_TRACE" ) ) { const size_t ntr = uf.size() + ub.size() + 1; CK( cudaMalloc( &c->dSwTrace, ntr * 5 * sizeof( unsigned long long ) ) ); CK( cudaMemset( c->dSwTrace, 0, ntr * 5 * sizeof( unsigned long long ) ) ); }
     if ( !c->dry && c->use_sweep ) { CK( cudaMalloc( &c->dSwCnt, ( size_t )c->sw_ncnt * sizeof( int ) ) ); CK( cudaMalloc( &c->dWg, ( ( size_t )c->sw_w_rows + 2 ) * 4 * 8 ) ); }
-    c->device_bytes += c->sw_tasks.bytes() + c->sw_units_f.bytes() + c->sw_units_b.bytes() + c->sw_ncnt * 4 + ( c->sw_w_rows + 2 ) * 32;
+    c->device_bytes += c->sw_tasks.bytes() + c->sw_units[0].bytes() + c->sw_units[1].bytes() + c->sw_inner.bytes() + c->sw_ncnt * 4 + ( c->sw_w_rows + 2 ) * 32;
   }
   c->device_bytes += c->gemm_tasks.bytes() + c->tiles_big.bytes() + c->tiles_small.bytes() + c->diag_tasks.bytes() + c->trsm_tasks.bytes() + c->trsm_tiles.bytes() +
                      c->asm_tasks.bytes() + c->sv_tasks.bytes() * 2 + c->sv_tiles_v.bytes() + c->sv_tiles_t.bytes() + c->sv_tiles_g.bytes() + c->rowidx.bytes() * 2 + c->sn.bytes();
@@ -1116,12 +1137,13 @@ static int sweep_persistent( b200_ctx* c, const double* d_b, int p, double* d_x,
   CK( cudaMemsetAsync( c->dSwCnt, 0, ( size_t )( c->sw_head + 2 ) * sizeof( int ), st ) );      /* counters and the two tickets; the error flag behind them is cleared once per solve */
   if ( c->sw_w_rows > 0 ) CK( cudaMemsetAsync( c->dWg, 0, ( size_t )c->sw_w_rows * pitch * 8, st ) );
   SweepArgs a;
-  a.cnt = c->dSwCnt; a.err = c->dSwCnt + c->sw_head + 2; a.tasks = c->sw_tasks.d; a.sn = c->sn.d; a.child_list = c->child_list.d; a.relidx = c->relidx.d; a.rowidx = c->rowidx.d;
+  a.cnt = c->dSwCnt; a.err = c->dSwCnt + c->sw_head + 2; a.tasks = c->sw_tasks.d; a.inner = c->sw_inner.d; a.sn = c->sn.d; a.child_list = c->child_list.d; a.relidx = c->relidx.d; a.rowidx = c->rowidx.d;
   a.Lf = c->dL; a.Lb = c->kind == B200_KIND_CHOLESKY ? c->dL : c->dU; a.sinvF = c->dSinvF; a.sinvB = c->dSinvB;
   a.B.b[0] = c->dY; a.B.b[1] = c->dZ; a.B.b[2] = c->dWg; a.B.b[3] = nullptr; a.p = p; a.pitch = pitch;
   const int pi = p <= 1 ? 0 : p <= 2 ? 1 : 2;
   for ( int dir = 0; dir < 2; dir++ ) {
-    a.units = dir == 0 ? c->sw_units_f.d : c->sw_units_b.d; a.nunits = ( int )( dir == 0 ? c->sw_units_f.n : c->sw_units_b.n ); a.head = c->dSwCnt + c->sw_head + dir;
+    a.units = c->sw_units[dir].d; a.nunits = ( int )c->sw_units[dir].n; a.head = c->dSwCnt + c->sw_head + dir;
+    a.trace = c->dSwTrace ? c->dSwTrace + ( dir == 0 ? 0 : 5 * c->sw_units[0].n ) : nullptr;
     if ( c->profile ) CK( cudaEventRecord( c->evp0, st ) );
     if ( pi == 0 ) launch_sweep<1>( c, a, c->sw_occ[0], st ); else if ( pi == 1 ) launch_sweep<2>( c, a, c->sw_occ[1], st ); else launch_sweep<4>( c, a, c->sw_occ[2], st );
     if ( c->profile ) { CK( cudaEventRecord( c->evp1, st ) ); CK( cudaEventSynchronize( c->evp1 ) ); float ms = 0; cudaEventElapsedTime( &ms, c->evp0, c->evp1 ); c->sprof_ms[SK_SWEEP_FWD + dir] += ms; c->sprof_n[SK_SWEEP_FWD + dir]++; }
@@ -1134,7 +1156,7 @@ static int sweep_persistent( b200_ctx* c, const double* d_b, int p, double* d_x,
 
 /* one pair of sweeps: d_x = (LL')^-1 d_b  (or (LU)^-1), launches counted into nl */
 static int sweep_once( b200_ctx* c, const double* d_b, int p, double* d_x, int64_t& nl ) {
-  if ( p <= 4 && c->use_sweep ) return sweep_persistent( c, d_b, p, d_x, nl );
+  if ( p <= c->sweep_pmax && c->use_sweep ) return sweep_persistent( c, d_b, p, d_x, nl );
   cudaStream_t st = c->stream;
   const int n = c->n;
   const int pitch = solve_pitch( p );
@@ -1602,6 +1624,16 @@ extern "C" int64_t b200_debug_sweep_tasks( b200_ctx_t* c, int64_t* out, int64_t 
   return n;
 }
 extern "C" int64_t b200_debug_sweep_counters( b200_ctx_t* c ) { return c ? c->sw_ncnt : -1; }
+/* diagnostics: per-unit time stamps of the last persistent sweep (context created with B200_SWEEP_TRACE set) and the device unit lists.
+ * trace: 5 uint64 per unit (globaltimer ns at start, clock64 at start / inputs ready / done, SM id); units: 16 ints each */
+extern "C" int64_t b200_debug_sweep_trace( b200_ctx_t* c, int dir, unsigned long long* trace, int* units, int64_t cap ) {
+  if ( !c || c->dry || !c->dSwTrace || dir < 0 || dir > 1 ) return -1;
+  cudaSetDevice( c->device );
+  const int64_t n = ( int64_t )c->sw_units[dir].n; const int64_t m = std::min( n, cap );
+  if ( trace && m > 0 ) cudaMemcpy( trace, c->dSwTrace + ( dir == 0 ? 0 : 5 * c->sw_units[0].n ), ( size_t )m * 5 * 8, cudaMemcpyDeviceToHost );
+  if ( units && m > 0 ) cudaMemcpy( units, c->sw_units[dir].d, ( size_t )m * 64, cudaMemcpyDeviceToHost );
+  return n;
+}
 extern "C" const char* b200_debug_kind_name( int kind ) { return kind >= 0 && kind < LK_COUNT ? kind_name[kind] : "?"; }
 
 /* every memory range a compute launch of the factor schedule may read or write, as conservative intervals of doubles inside

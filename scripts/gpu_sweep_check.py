@@ -1,6 +1,7 @@
 """persistent sweeps (p <= 4) against the level-set FMA path (B200_SOLVE_LEVELSET=1) and the tensor path (p = 8): bit identity on small
 grids, then timings at a large one: python scripts/gpu_sweep_check.py [big_grid]"""
 import sys, os, time, numpy as np
+os.environ["B200_SWEEP_PMAX"] = "4"      # the persistent path for every p <= 4 (production uses it for p = 1)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 m = g.load_package()

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 UK_FWD_GATHER, UK_FWD_SMALL, UK_GEMV, UK_GEMVT, UK_BWD_SMALL = range(5)
-FIELDS = ("kind", "task", "o0", "aux", "sn", "w1", "n1", "v1", "w2", "v2", "sig", "dn", "dtot", "up")
+FIELDS = ("kind", "task", "o0", "aux", "sn", "w1", "n1", "v1", "w2", "v2", "sig", "up")
 
 
 def export(mc, S):
@@ -74,7 +74,8 @@ def accesses(u, tasks, sy):
         vsel, voff, K, dsel, doff, N, tri, mode = (int(x) for x in tasks[task])
         cols = np.arange(o0, min(o0 + 64, N))
         if aux:
-            ri = sy.rowidx[sy.rowptr[sn] + k: sy.rowptr[sn] + k + K].astype(np.int64)
+            ri = sy.rowidx[sy.rowptr[sn] + k + voff: sy.rowptr[sn] + k + voff + K].astype(np.int64)
+            assert len(ri) == K
             rd = vsel * BASE + ri
         else:
             rd = vsel * BASE + voff + np.arange(K)
@@ -112,60 +113,51 @@ def accesses(u, tasks, sy):
 def check(units, tasks, sy, ncnt, direction):
     """the three properties for one sweep; raises AssertionError with the offending unit; returns some statistics"""
     N = len(units)
-    U = [dict(zip(FIELDS, (int(x) for x in units[i][:14]))) for i in range(N)]
-    # signallers of every counter, in list order; supernode-complete events are virtual nodes N + sn
+    U = [dict(zip(FIELDS, (int(x) for x in units[i][:12]))) for i in range(N)]
+    # signallers of every counter, in list order: a unit adds 1 to cnt[sig] (a tile / product counter) and 1 to cnt[up] (a completion counter)
     sig = {}
     for i, u in enumerate(U):
-        if u["sig"] >= 0: sig.setdefault(u["sig"], []).append(i)
-    members = {}
-    for i, u in enumerate(U): members.setdefault(u["sn"], []).append(i)
-    for sn, ms in members.items():
-        assert all(U[i]["dtot"] == len(ms) for i in ms), f"supernode {sn}: dtot differs from its number of units"
-        assert len({U[i]["dn"] for i in ms}) == 1 and len({U[i]["up"] for i in ms}) == 1
-        up = U[ms[0]]["up"]
-        if up >= 0: sig.setdefault(up, []).append(N + sn)
-    last_member = {sn: ms[-1] for sn, ms in members.items()}
-    for c, lst in sig.items():
+        if u["sig"] >= 0: sig.setdefault(u["sig"], []).append((i, 1))
+        if u["up"] >= 0: sig.setdefault(u["up"], []).append((i, 1))
+    for c in sig:
         assert 0 <= c < ncnt
-        kinds = {x >= N for x in lst}
-        assert len(kinds) == 1, f"counter {c} is raised both by units and by supernode completions"
-    # pass 1: happens-before sets under the intended meaning of every wait
+    # pass 1: happens-before sets under the intended meaning of every wait: cnt[c] >= v stands for the shortest prefix (in list order) of c's
+    # signallers whose contributions add up to v -- and they must add up to v EXACTLY, so that no other subset can reach it without them
     HB = {}
     waits = [[] for _ in range(N)]          # per unit: list of (counter, v)
+    prefix_cache = {}
 
     def preds_of(i, c, v):
-        lst = sig.get(c, [])
-        assert v <= len(lst), f"unit {i} waits for cnt[{c}] >= {v} but only {len(lst)} signals exist: it would never run"
-        return lst[:v]
+        if (c, v) not in prefix_cache:
+            lst = sig.get(c, [])
+            tot = 0; m = 0
+            while m < len(lst) and tot < v:
+                tot += lst[m][1]; m += 1
+            assert tot == v, f"unit {i} waits for cnt[{c}] >= {v}: the signals of its first {m} signallers add up to {tot}, not {v}"
+            prefix_cache[(c, v)] = m
+        return [d for d, w in sig[c][:prefix_cache[(c, v)]]]
     for i, u in enumerate(U):
         hb = 0
         ws = [(u["w1"] + j, u["v1"]) for j in range(u["n1"])] + ([(u["w2"], u["v2"])] if u["w2"] >= 0 else [])
+        assert all(w[1] >= 0 for w in ws), f"unit {i}: a wait value was never filled in"
         waits[i] = [w for w in ws if w[1] > 0]
         for c, v in waits[i]:
             for d in preds_of(i, c, v):
-                if d >= N:
-                    assert last_member[d - N] < i, f"unit {i} waits for the completion of supernode {d - N}, whose units follow it in the list (deadlock)"
-                else:
-                    assert d < i, f"unit {i} waits for unit {d}, which follows it in the list (deadlock)"
+                assert d < i, f"unit {i} waits for unit {d}, which follows it in the list (deadlock)"
                 hb |= HB[d] | (1 << d)
         HB[i] = hb
-        sn = u["sn"]
-        if last_member[sn] == i:
-            e = 0
-            for j in members[sn]: e |= HB[j] | (1 << j)
-            HB[N + sn] = e
-    # pass 2: a wait for v of m > v signals is sound only if every later signaller happens-after the first v
+    # pass 2: a wait for a proper prefix of the signallers is sound only if every later signaller happens-after the whole prefix
     seen = set()
     for i in range(N):
         for c, v in waits[i]:
             if (c, v) in seen: continue
             seen.add((c, v))
-            lst = sig[c]
-            if v == len(lst): continue
+            lst = sig[c]; m = prefix_cache[(c, v)]
+            if m == len(lst): continue
             first = 0
-            for d in lst[:v]: first |= 1 << d
-            for d in lst[v:]:
-                assert d in HB and (HB[d] & first) == first, f"cnt[{c}] >= {v} (unit {i}) can be satisfied by signaller {d} before the first {v} signallers are done"
+            for d, w in lst[:m]: first |= 1 << d
+            for d, w in lst[m:]:
+                assert d in HB and (HB[d] & first) == first, f"cnt[{c}] >= {v} (unit {i}) can be satisfied by signaller {d} before the first {m} signallers are done"
     # pass 3: data races
     lastw = {}; readers = {}
     nconf = 0

@@ -446,3 +446,31 @@ def test_headline_shape_properties_at_64cubed(mc):
         tr += float((np.tril(p[:k]) ** 2).sum() + (p[k:] ** 2).sum())
     assert abs(tr - 6.0 * n) <= 1e-9 * 6.0 * n          # ||L||_F^2 = trace(A)
     s.close()
+
+
+@pytest.mark.parametrize("kind", ["cholesky", "lu"])
+def test_persistent_sweeps_same_bits_as_level_set_and_tensor_sweeps(mc, kind, monkeypatch):
+    """the sweeps exist three times: level-set launches of FMA kernels (p = 2..4), ONE persistent kernel per sweep whose units wait on
+    device-side counters (p = 1 in production; csrc/cuda/b200_sweep.cuh) and the tensor path (p >= 5).  All three follow one canonical
+    arithmetic: a column has the same bits whichever of them solves it.  B200_SWEEP_PMAX / B200_SOLVE_LEVELSET select the path."""
+    if kind == "cholesky":
+        n, cp, ri, v = stencils.poisson3d_upper(30); k = mc.KIND_CHOLESKY
+    else:
+        n, cp, ri, v = stencils.convdiff27_full(16); k = mc.KIND_LU
+    rng = np.random.default_rng(11); B = rng.standard_normal((n, 8))
+    out = {}
+    for name, env in (("persistent", {"B200_SWEEP_PMAX": "4"}), ("levelset", {"B200_SOLVE_LEVELSET": "1"})):
+        for key in ("B200_SWEEP_PMAX", "B200_SOLVE_LEVELSET"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        s = mc.Solver(); s.analyze(n, cp, ri, k)
+        s.L.b200_set_refinement(s.ctx, 0)
+        assert s.factor(v) == 0
+        out[name] = [s.solve(np.asfortranarray(B[:, :p]) if p > 1 else B[:, 0].copy()).reshape(n, -1, order="F") for p in (1, 2, 3, 4)]
+        if name == "persistent":
+            out["tensor"] = s.solve(np.asfortranarray(B)).reshape(n, -1, order="F")
+        s.close()
+    for i, p in enumerate((1, 2, 3, 4)):
+        assert np.array_equal(out["persistent"][i], out["levelset"][i]), f"p={p}: persistent and level-set sweeps differ"
+        assert np.array_equal(out["persistent"][i], out["tensor"][:, :p]), f"p={p}: persistent sweeps and the tensor path differ"

@@ -19,6 +19,7 @@ CASES = [
     ("poisson2d_130x7", lambda: stencils.poisson2d_upper(130, 7), 0),
     ("convdiff27_14_lu", lambda: stencils.convdiff27_full(14), 1),
     ("single_unknown", lambda: stencils.poisson2d_upper(1, 1), 0),
+    ("poisson3d_34", lambda: stencils.poisson3d_upper(34), 0),
 ]
 
 
