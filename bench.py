@@ -279,14 +279,16 @@ def main():
     if world > 1:
         s.join(rank, world, dist=dist)
     host_threads = max(1, (os.cpu_count() or 8) // world)
+    # rank 0 orders with all host cores (N > 1: and broadcasts the permutation); every rank then runs the symbolic analysis on the GIVEN permutation.
+    # N = 1 takes the same two steps, so that every N factors the very same supernodal tree and the checksums below can be compared across the N lines
+    # (the analysis is not idempotent on its own output permutation: postorder and amalgamation renumber the columns).  analyze_s is the first step,
+    # which is what the plugin's solver_analyze does; the second step is reported as reanalyze_s.
     t0 = time.perf_counter()
-    if world > 1:   # rank 0 orders with all host cores and broadcasts the permutation; every rank then runs the same symbolic analysis on it
-        perm = m.shared_ordering(n, cp, ri, KIND, rank, world, dist, threads=os.cpu_count() or 8)
-        S = s.analyze(n, cp, ri, KIND, perm=perm, threads=host_threads)
-    else:
-        perm = None
-        S = s.analyze(n, cp, ri, KIND, threads=host_threads)
+    perm = m.shared_ordering(n, cp, ri, KIND, rank, world, dist, threads=os.cpu_count() or 8)
     t_analyze = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    S = s.analyze(n, cp, ri, KIND, perm=perm, threads=host_threads)
+    t_reanalyze = time.perf_counter() - t0
     F = S.flops * (2.0 if LU else 1.0)
     ctx = s.ctx
     d_vals = L.b200_dev_alloc(ctx, v.nbytes); L.b200_dev_upload(ctx, d_vals, v.ctypes.data, v.nbytes)
@@ -387,7 +389,7 @@ def main():
         u_ = f_ - k_; ea_bytes = float(16.0 * (u_ * (u_ + 1) / 2).sum())
         if world > 1:
             prof["extend_add"] = (0, 0.0)      # whole-tree bytes over one rank's time is not a rate: reported at N=1 only
-        extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "backward_error": berr,
+        extra = {"factor_s": factor_s, "solve_s": solve_s, "factor_plus_solve_s": factor_s + solve_s, "analyze_s": t_analyze, "reanalyze_s": t_reanalyze, "backward_error": berr,
                  "n": n, "nnz_L": int(S.nnzL), "stored_nnz_L": int(S.stored_nnzL), "factor_flops": F, "supernodes": S.ns, "levels": S.maxdepth + 1, "max_front": S.maxfront,
                  "device_gb": st.device_bytes / 1e9, "solve_hbm_gbs": (16.0 * S.nnzL + 32.0 * n) * (1 + refine[0]) / solve_s / 1e9, "refine_steps": refine[0], "nccl_bytes_per_factor": nvlink_bytes,
                  "extend_add_roofline": {"bound": "hbm", "kernel": "extend_add_kernel", "achieved": ea_bytes / (prof["extend_add"][1] * 1e-3) / 1e9 if prof.get("extend_add", (0, 0))[1] > 0 else None,

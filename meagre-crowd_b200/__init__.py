@@ -283,12 +283,12 @@ def shared_ordering(n, colptr, rowidx, kind, rank, world, dist, threads=0):
     (torch.distributed), so that N ranks do not run N copies of the most expensive host step on N-times fewer cores each.
     Every rank (rank 0 included) then runs the rest of the analysis on the GIVEN permutation -- the same code path
     everywhere, hence bit-identical symbolic structures.  Returns the permutation (numpy int32)."""
-    import torch
     if world == 1:
         S = analyze(n, colptr, rowidx, kind, threads=threads)
         perm = sym_array(S, "perm", n, np.int32).copy()
         lib().b200_symbolic_free(S)
         return perm
+    import torch
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     if rank == 0:
         S = analyze(n, colptr, rowidx, kind, threads=threads)
