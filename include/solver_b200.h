@@ -242,7 +242,6 @@ int b200_debug_read( b200_ctx_t* c, int which, double* dst, int64_t offset, int6
 
 /* micro-benchmarks used to establish the FP64 roof on the box */
 double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ); /* our DMMA kernel */
-double b200_bench_dgemm_variant( b200_ctx_t* c, int variant, int m, int n, int k, int iters );   /* tile-shape tuning aid (cp.async kernel) */
 double b200_bench_dgemm_bulk_variant( b200_ctx_t* c, int variant, int m, int n, int k, int iters );   /* the same for the bulk-copy kernel */
 double b200_bench_dmma_occupancy( b200_ctx_t* c, int warps_per_sm, int ilp );   /* DMMA rate vs resident warps / independent accumulators */
 double b200_bench_fp64_peak_tflops( b200_ctx_t* c, int which, int iters );  /* 0: DMMA.8x8x4 issue roof, 1: DFMA roof */

@@ -103,7 +103,7 @@ EXPORTED_SYMBOLS = [
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_upload_symbolic", "b200_factor_host", "b200_factor_device",
     "b200_solve_host", "b200_solve_device", "b200_dev_alloc", "b200_dev_free", "b200_dev_upload", "b200_dev_download",
     "b200_host_alloc_pinned", "b200_host_free_pinned", "b200_dev_sync", "b200_flush_l2", "b200_get_stats", "b200_set_profile",
-    "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dgemm_variant", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
+    "b200_get_profile", "b200_debug_read", "b200_set_refinement", "b200_bench_dgemm_tflops", "b200_bench_dmma_occupancy", "b200_bench_fp64_peak_tflops", "b200_bench_stream_gbs",
     "b200_outer_width", "b200_set_outer_width_cap", "b200_plan_create", "b200_plan_free", "b200_plan_col_owner", "b200_plan_member", "b200_plan_cb_transfers",
     "b200_mg_unique_id", "b200_mg_init", "b200_mg_rank", "b200_bench_potrf_us", "b200_bench_dgemm_bulk_variant", "b200_ctx_create_dry", "b200_debug_schedule", "b200_debug_messages", "b200_debug_kind_name", "b200_debug_accesses", "b200_factor_colnorms", "b200_debug_sweep_units", "b200_debug_sweep_tasks", "b200_debug_sweep_counters", "b200_debug_sweep_trace",
 ]
@@ -197,7 +197,6 @@ def lib():
     L.b200_bench_potrf_us.restype = dbl; L.b200_bench_potrf_us.argtypes = [vp, i32, i32, i32, i32]
     L.b200_bench_dgemm_bulk_variant.restype = dbl; L.b200_bench_dgemm_bulk_variant.argtypes = [vp, i32, i32, i32, i32, i32]
     L.b200_bench_dgemm_tflops.restype = dbl; L.b200_bench_dgemm_tflops.argtypes = [vp, i32, i32, i32, i32]
-    L.b200_bench_dgemm_variant.restype = dbl; L.b200_bench_dgemm_variant.argtypes = [vp, i32, i32, i32, i32, i32]
     L.b200_bench_dmma_occupancy.restype = dbl; L.b200_bench_dmma_occupancy.argtypes = [vp, i32, i32]
     L.b200_bench_fp64_peak_tflops.restype = dbl; L.b200_bench_fp64_peak_tflops.argtypes = [vp, i32, i32]
     L.b200_bench_stream_gbs.restype = dbl; L.b200_bench_stream_gbs.argtypes = [vp, C.c_size_t, i32]

@@ -11,9 +11,9 @@
  *   potrf_diag         <=64x64 diagonal block Cholesky + triangular inverse     (latency)
  *   getrf_diag         <=64x64 diagonal block LU, partial pivoting inside it   (latency)
  *   trsm_rows          panel rows x inverse diagonal block                     (FP64)
- *   gemm_nt_dmma       C -= A * B'  on FP64 tensor-core tiles
+ *   gemm_nt_dmma_bulk  C -= A * B'  on FP64 tensor-core tiles
  *                      (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no
- *                      f64 kind), operands staged with cp.async multi-stage    (FP64 roof)
+ *                      f64 kind), operands staged by cp.async.bulk + mbarriers (FP64 roof)
  *   solve kernels      level-set forward/backward sweeps over supernode blocks (HBM bound)
  */
 #pragma once
@@ -644,149 +644,19 @@ __global__ void __launch_bounds__( 256 ) trsm_rows_kernel( const TrsmTask* __res
   }
 }
 
-/* ---------------------------------------------------------- DMMA GEMM NT
- * C[M x N] -= A[M x K] * B[N x K]'   (all column-major).
- * CTA tile BM x BN, K step 16, STAGES-deep cp.async pipeline.  Shared tiles are
- * stored k-major with a row stride of BM+4 doubles so that the m8n8k4 fragment
- * reads (lane>>2 -> m, lane&3 -> k) hit 32 distinct banks.  Each warp owns a
- * WM x WN sub-tile = (WM/8)x(WN/8) DMMA.8x8x4 accumulators in registers. */
-template <int BM, int BN, int WM, int WN, int STAGES, int BK = 16>
-__global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 ) gemm_nt_dmma_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles ) {
-  constexpr int NT = ( BM / WM ) * ( BN / WN ) * 32;
-  constexpr int LDA = BM + 4, LDB = BN + 4;
-  constexpr int MT = WM / 8, NTL = WN / 8;
-  extern __shared__ double sm[];
-  double* As = sm;                         /* [STAGES][BK][LDA] */
-  double* Bs = sm + STAGES * BK * LDA;     /* [STAGES][BK][LDB] */
-  const Tile tl = tiles[blockIdx.x];
-  const GemmTask t = tasks[tl.task];
-  const int m0 = tl.tm * BM, n0 = tl.tn * BN;
-  const int mrem = t.M - m0, nrem = t.N - n0;
-  const double* Ag = t.A + m0;
-  const double* Bg = t.B + n0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
-  /* 16-byte cp.async needs 16-byte aligned sources.  Leading dimensions are even by construction; when
-   * the tile's first row sits at an odd offset the whole tile is fetched one row early (that row is
-   * valid memory of the same panel column and is never read back) and every fragment read is shifted.
-   * Each thread owns a fixed set of 16-byte chunks: all address arithmetic happens once, before the
-   * K loop; per stage only the pointers advance (the issue slots belong to DMMA, not to IMAD). */
-  const bool a16 = ( t.lda & 1 ) == 0, b16 = ( t.ldb & 1 ) == 0;
-  const int sa = a16 ? ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ) : 0, sb = b16 ? ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 ) : 0;
-  const int K = t.K;
-  const int nk = ( K + BK - 1 ) / BK;
-  constexpr int TPC = NT / BK;                      /* threads per k-column                      */
-  constexpr int ACH = ( BM / 2 + TPC ) / TPC;       /* chunks per thread (incl. the shift chunk) */
-  constexpr int BCH = ( BN / 2 + TPC ) / TPC;
-  static_assert( NT % BK == 0, "threads must tile the k-columns" );
-  const int lq = tid / TPC, lc = tid % TPC;         /* my k-column inside a stage, my first chunk */
-  const double* gA[ACH]; int bA[ACH]; int oA[ACH];
-  const double* gB[BCH]; int bB[BCH]; int oB[BCH];
-#pragma unroll
-  for ( int j = 0; j < ACH; j++ ) {
-    const int r2 = 2 * ( lc + TPC * j ), r = r2 - sa;
-    const bool in = r2 < BM + 2 * sa;
-    bA[j] = !in ? -1 : ( r < mrem ) ? ( r + 1 < mrem ? 16 : 8 ) : 0;     /* -1: slot does not exist */
-    gA[j] = bA[j] > 0 ? Ag + r + ( int64_t )lq * t.lda : t.A;
-    oA[j] = lq * LDA + r2;
-  }
-#pragma unroll
-  for ( int j = 0; j < BCH; j++ ) {
-    const int r2 = 2 * ( lc + TPC * j ), r = r2 - sb;
-    const bool in = r2 < BN + 2 * sb;
-    bB[j] = !in ? -1 : ( r < nrem ) ? ( r + 1 < nrem ? 16 : 8 ) : 0;
-    gB[j] = bB[j] > 0 ? Bg + r + ( int64_t )lq * t.ldb : t.B;
-    oB[j] = lq * LDB + r2;
-  }
-  const int64_t stepA = ( int64_t )BK * t.lda, stepB = ( int64_t )BK * t.ldb;
-
-  auto load_stage = [&]( int stage, int k0 ) {
-    double* as = As + stage * BK * LDA;
-    double* bs = Bs + stage * BK * LDB;
-    const bool kin = k0 + lq < K;
-    if ( a16 ) {
-#pragma unroll
-      for ( int j = 0; j < ACH; j++ ) if ( bA[j] >= 0 ) { cp_async16( as + oA[j], gA[j], kin ? bA[j] : 0 ); if ( bA[j] > 0 ) gA[j] += stepA; }
-    } else {
-      for ( int c = tid; c < BK * BM; c += NT ) {
-        const int q = c / BM, r = c % BM;
-        const int kq = k0 + q;
-        int bytes = ( kq < K && r < mrem ) ? 8 : 0;
-        cp_async8( as + q * LDA + r, bytes ? ( const void* )( Ag + r + ( int64_t )kq * t.lda ) : ( const void* )t.A, bytes );
-      }
-    }
-    if ( b16 ) {
-#pragma unroll
-      for ( int j = 0; j < BCH; j++ ) if ( bB[j] >= 0 ) { cp_async16( bs + oB[j], gB[j], kin ? bB[j] : 0 ); if ( bB[j] > 0 ) gB[j] += stepB; }
-    } else {
-      for ( int c = tid; c < BK * BN; c += NT ) {
-        const int q = c / BN, r = c % BN;
-        const int kq = k0 + q;
-        int bytes = ( kq < K && r < nrem ) ? 8 : 0;
-        cp_async8( bs + q * LDB + r, bytes ? ( const void* )( Bg + r + ( int64_t )kq * t.ldb ) : ( const void* )t.B, bytes );
-      }
-    }
-  };
-
-  double acc[MT][NTL][2];
-#pragma unroll
-  for ( int i = 0; i < MT; i++ )
-#pragma unroll
-    for ( int j = 0; j < NTL; j++ ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-
-#pragma unroll
-  for ( int s = 0; s < STAGES - 1; s++ ) { if ( s < nk ) load_stage( s, s * BK ); cp_async_commit(); }
-
-  const int fr = lane >> 2, fk = lane & 3;
-  for ( int kt = 0; kt < nk; kt++ ) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    { const int nx = kt + STAGES - 1; if ( nx < nk ) load_stage( nx % STAGES, nx * BK ); cp_async_commit(); }
-    const double* as = As + ( kt % STAGES ) * BK * LDA + wm0 + fr + sa;
-    const double* bs = Bs + ( kt % STAGES ) * BK * LDB + wn0 + fr + sb;
-#pragma unroll
-    for ( int kk = 0; kk < BK; kk += 4 ) {
-      double af[MT], bf[NTL];
-#pragma unroll
-      for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
-#pragma unroll
-      for ( int j = 0; j < NTL; j++ ) bf[j] = bs[( kk + fk ) * LDB + j * 8];
-#pragma unroll
-      for ( int i = 0; i < MT; i++ )
-#pragma unroll
-        for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
-    }
-  }
-  cp_async_wait<0>();
-
-  /* epilogue: C -= acc (read-modify-write, masked to the stored triangle) */
-  double* Cg = t.C;
-#pragma unroll
-  for ( int j = 0; j < NTL; j++ ) {
-#pragma unroll
-    for ( int h = 0; h < 2; h++ ) {
-      const int c = n0 + wn0 + j * 8 + 2 * fk + h;
-      if ( c < t.N ) {
-        double* cc = Cg + ( int64_t )c * t.ldc;
-#pragma unroll
-        for ( int i = 0; i < MT; i++ ) {
-          const int r = m0 + wm0 + i * 8 + fr;
-          if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
-        }
-      }
-    }
-  }
-}
-
 /* ------------------------------------------- DMMA GEMM NT, bulk-copy pipeline
- * Same product and the same shared-memory layout as gemm_nt_dmma_kernel, but the operand tiles are
- * brought in by the async proxy: one elected producer thread issues, per stage, one
- * cp.async.bulk (SASS UBLKCP) per k-column of A and of B -- each column of a panel tile is a contiguous
- * run of <=66 doubles -- and the bytes are counted on an mbarrier.  The 8 consumer warps only ever wait
- * on "full[stage]" and signal "empty[stage]": there is no block-wide barrier in the K loop, so a warp
- * that gets ahead keeps the FP64 tensor pipe busy instead of waiting for the slowest one
- * (ncu on the cp.async version: 13 % of all warp samples sat at the per-stage __syncthreads()).
- * Requirements (true for every factor task): lda, ldb even; panel columns padded to their even ld. */
+ * C[M x N] -= A[M x K] * B[N x K]'   (all column-major; mode 1: C = A B').
+ * CTA tile BM x BN, K step 16, STAGES-deep pipeline.  Shared tiles are stored k-major with a row stride of BM+4 doubles so that the
+ * m8n8k4 fragment reads (lane>>2 -> m, lane&3 -> k) hit 32 distinct banks; each warp owns a WM x WN sub-tile = (WM/8)x(WN/8)
+ * DMMA.8x8x4 accumulators in registers.  The operand tiles are brought in by the async proxy: one elected producer warp issues, per
+ * stage, one cp.async.bulk (SASS UBLKCP) per k-column of A and of B -- each column of a panel tile is a contiguous run of <=66
+ * doubles -- and the bytes are counted on an mbarrier.  The 8 consumer warps only ever wait on "full[stage]" and signal
+ * "empty[stage]": there is no block-wide barrier in the K loop, so a warp that gets ahead keeps the FP64 tensor pipe busy instead of
+ * waiting for the slowest one (ncu on a cp.async + __syncthreads version: 13 % of all warp samples sat at the per-stage barrier).
+ * A tile whose first row sits at an odd address is fetched one element early (16-byte aligned bulk copies) and every fragment read
+ * is shifted.  Requirements (true for every factor task): lda, ldb even; panel columns padded to their even ld.
+ * Tried and measured slower (profiles/r1_gemm_bulk_variants.txt, r1_gemm_variants_*.txt): 128x128 and 128x64 tiles at small K, 6 stages,
+ * a persistent-CTA variant with a static tile order (28.3 against 32.9 TFLOP/s at K = 512, 752 against 673 ms per 128^3 factorization). */
 __device__ __forceinline__ void mbar_init( uint64_t* bar, int count ) {
   asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"( ( unsigned )__cvta_generic_to_shared( bar ) ), "r"( count ) );
 }
@@ -902,118 +772,6 @@ __global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt
         for ( int i = 0; i < MT; i++ ) {
           const int r = m0 + wm0 + i * 8 + fr;
           if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
-        }
-      }
-    }
-  }
-}
-
-/* ------------------------------------------- DMMA GEMM NT, persistent CTAs
- * The bulk-copy kernel above pays the fill of its 4-stage pipeline once per 64x64 tile; with K = 128..256 (mid tree
- * levels, in-panel updates) that bubble is a large share of the tile (21 TFLOP/s at K = 128 against 33 at K = 512).
- * Here a CTA walks over tiles ti = blockIdx.x, blockIdx.x + gridDim.x, ...: the producer warp never stops at a tile
- * boundary -- while the consumer warps write back tile i it is already filling the stages with tile i+1 -- and the
- * mbarrier phases simply keep counting k-steps across tiles.  Same shared-memory layout, same arithmetic order.
- * EXPERIMENTAL (env B200_GEMM_PERSISTENT=1): with a static round-robin tile assignment it measured 22.1 / 18.8 TFLOP/s
- * at K = 128 / 64 (one-tile kernel: 21.1 / 15.0) but only 28.3 at K = 512 (32.9), and a slower 128^3 factorization
- * (752 vs 673 ms), so the one-tile-per-CTA kernel stays the production path. */
-template <int BM, int BN, int WM, int WN, int STAGES>
-__global__ void __launch_bounds__( ( BM / WM ) * ( BN / WN ) * 32 + 32 ) gemm_nt_dmma_pers_kernel( const GemmTask* __restrict__ tasks, const Tile* __restrict__ tiles, int ntiles,
-                                                                                               const double* __restrict__ zeros ) {
-  constexpr int BK = 16;
-  constexpr int NCW = ( BM / WM ) * ( BN / WN );
-  constexpr int LDA = BM + 4, LDB = BN + 4;
-  constexpr int MT = WM / 8, NTL = WN / 8;
-  extern __shared__ double sm[];
-  double* As = sm;
-  double* Bs = sm + STAGES * BK * LDA;
-  uint64_t* full = reinterpret_cast<uint64_t*>( sm + STAGES * BK * ( LDA + LDB ) );
-  uint64_t* empty = full + STAGES;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ( tid == 0 ) {
-    for ( int s = 0; s < STAGES; s++ ) { mbar_init( &full[s], 1 ); mbar_init( &empty[s], NCW ); }
-    asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
-    asm volatile( "fence.proxy.async.shared::cta;\n" ::: "memory" );
-  }
-  __syncthreads();
-  unsigned g = 0;                                   /* k-steps issued / consumed so far by this CTA, over all its tiles */
-  if ( warp == NCW ) {
-    /* ---------------- producer warp */
-    const int q = lane & 15; const bool isb = lane >= 16;
-    for ( int ti = blockIdx.x; ti < ntiles; ti += gridDim.x ) {
-      const Tile tl = tiles[ti];
-      const GemmTask t = tasks[tl.task];
-      const int m0 = tl.tm * BM, n0 = tl.tn * BN;
-      const int mrem = t.M - m0, nrem = t.N - n0;
-      const double* Ag = t.A + m0;
-      const double* Bg = t.B + n0;
-      const int sa = ( int )( ( ( uintptr_t )Ag >> 3 ) & 1 ), sb = ( int )( ( ( uintptr_t )Bg >> 3 ) & 1 );
-      const int K = t.K, nk = ( K + BK - 1 ) / BK;
-      const int ra = ( ( min( BM, mrem ) + sa + 1 ) & ~1 ) * 8, rb = ( ( min( BN, nrem ) + sb + 1 ) & ~1 ) * 8;
-      const double* gsrc = isb ? Bg - sb : Ag - sa;
-      const int64_t ldg = isb ? t.ldb : t.lda;
-      const int bytes = isb ? rb : ra;
-      for ( int kt = 0; kt < nk; kt++, g++ ) {
-        const unsigned slot = g % STAGES, use = g / STAGES;
-        if ( lane == 0 ) {
-          if ( use > 0 ) mbar_wait( &empty[slot], ( use - 1 ) & 1 );
-          mbar_expect_tx( &full[slot], BK * ( ra + rb ) );
-        }
-        __syncwarp();
-        double* dst = isb ? Bs + slot * BK * LDB + q * LDB : As + slot * BK * LDA + q * LDA;
-        const int kq = kt * BK + q;
-        bulk_g2s( dst, kq < K ? ( const void* )( gsrc + ( int64_t )kq * ldg ) : ( const void* )zeros, bytes, &full[slot] );
-      }
-    }
-    return;
-  }
-  /* ---------------- consumers */
-  const int wm0 = ( warp % ( BM / WM ) ) * WM, wn0 = ( warp / ( BM / WM ) ) * WN;
-  const int fr = lane >> 2, fk = lane & 3;
-  for ( int ti = blockIdx.x; ti < ntiles; ti += gridDim.x ) {
-    const Tile tl = tiles[ti];
-    const GemmTask t = tasks[tl.task];
-    const int m0 = tl.tm * BM, n0 = tl.tn * BN;
-    const int sa = ( int )( ( ( uintptr_t )( t.A + m0 ) >> 3 ) & 1 ), sb = ( int )( ( ( uintptr_t )( t.B + n0 ) >> 3 ) & 1 );
-    const int nk = ( t.K + BK - 1 ) / BK;
-    double acc[MT][NTL][2];
-#pragma unroll
-    for ( int i = 0; i < MT; i++ )
-#pragma unroll
-      for ( int j = 0; j < NTL; j++ ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    for ( int kt = 0; kt < nk; kt++, g++ ) {
-      const unsigned slot = g % STAGES;
-      mbar_wait( &full[slot], ( g / STAGES ) & 1 );
-      const double* as = As + slot * BK * LDA + wm0 + fr + sa;
-      const double* bs = Bs + slot * BK * LDB + wn0 + fr + sb;
-#pragma unroll
-      for ( int kk = 0; kk < BK; kk += 4 ) {
-        double af[MT], bf[NTL];
-#pragma unroll
-        for ( int i = 0; i < MT; i++ ) af[i] = as[( kk + fk ) * LDA + i * 8];
-#pragma unroll
-        for ( int j = 0; j < NTL; j++ ) bf[j] = bs[( kk + fk ) * LDB + j * 8];
-#pragma unroll
-        for ( int i = 0; i < MT; i++ )
-#pragma unroll
-          for ( int j = 0; j < NTL; j++ ) dmma884( acc[i][j][0], acc[i][j][1], af[i], bf[j] );
-      }
-      __syncwarp();
-      if ( lane == 0 ) mbar_arrive( &empty[slot] );
-    }
-    double* Cg = t.C;
-#pragma unroll
-    for ( int j = 0; j < NTL; j++ ) {
-#pragma unroll
-      for ( int h = 0; h < 2; h++ ) {
-        const int c = n0 + wn0 + j * 8 + 2 * fk + h;
-        if ( c < t.N ) {
-          double* cc = Cg + ( int64_t )c * t.ldc;
-#pragma unroll
-          for ( int i = 0; i < MT; i++ ) {
-            const int r = m0 + wm0 + i * 8 + fr;
-            if ( r < t.M && ( !t.lower || r + t.diag >= c ) ) { if ( t.mode ) cc[r] = acc[i][j][h]; else cc[r] -= acc[i][j][h]; }
-          }
         }
       }
     }

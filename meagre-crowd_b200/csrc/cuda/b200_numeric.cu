@@ -74,13 +74,12 @@ static int load_nccl() {
 static inline int outer_width( int maxfront ) { return b200_outer_width( maxfront ); }
 constexpr int ASM_COLS = 32;  /* destination columns per extend-add CTA */
 constexpr int GEMM_STAGES = 4;
-/* production tile of the DMMA update kernel: 64x64 per CTA, 8 warps of 32x16, 4-stage cp.async pipeline.
+/* production tile of the DMMA update kernel: 64x64 per CTA, 8 warps of 32x16, 4-stage bulk-copy pipeline.
  * 69 KB of shared memory and <=80 registers keep 3 CTAs (24 warps) resident per SM, which measured
  * 28-31 TFLOP/s against 17-23 for a 128x128 tile with one CTA per SM (profiles/r1_gemm_variants.txt). */
 #define GEMM_CFG 64, 64, 32, 16, GEMM_STAGES
 constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_THREADS = 256;
-constexpr int BIG_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8;
-constexpr int BULK_SMEM = BIG_SMEM + 2 * GEMM_STAGES * 8;   /* + full/empty mbarriers */
+constexpr int BULK_SMEM = GEMM_STAGES * 16 * ( 68 + 68 ) * 8 + 2 * GEMM_STAGES * 8;   /* k-major A and B tiles of every stage + full/empty mbarriers */
 constexpr int BULK_THREADS = GEMM_THREADS + 32;             /* + the producer warp */
 constexpr int SVG_SMEM_NT = GEMM_STAGES * 16 * ( 68 + 68 ) * 8 + 2 * GEMM_STAGES * 8;                 /* gemm_solve_dmma_kernel<false> */
 constexpr int SVG_SMEM_BT = 3 * ( 32 * 68 + 64 * 36 ) * 8 + 2 * 3 * 8;                                /* gemm_solve_dmma_kernel<true>: BK = 32, 3 stages */
@@ -132,7 +131,7 @@ struct b200_ctx {
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
   double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
-  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; int* dViol = nullptr; double pivot_threshold = 0.1; bool use_bulk = true, use_pers = false, use_small_front = true, replicate = false; DevVec<int> small_sns; int pers_grid = 444;
+  int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; int* dViol = nullptr; double pivot_threshold = 0.1; bool use_small_front = true, replicate = false; DevVec<int> small_sns;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
   unsigned long long* dOmega = nullptr;
@@ -184,12 +183,8 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) ); CKN( cudaEventCreateWithFlags( &c->evs2, cudaEventDisableTiming ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) ); CKN( cudaMalloc( &c->dViol, sizeof( int ) ) );
   { const char* e = getenv( "B200_PIVOT_THRESHOLD" ); if ( e && atof( e ) > 0.0 && atof( e ) <= 1.0 ) c->pivot_threshold = atof( e ); }
-  CKN( cudaFuncSetAttribute( gemm_nt_dmma_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM ) );
   CKN( cudaFuncSetAttribute( gemm_nt_dmma_bulk_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
-  CKN( cudaFuncSetAttribute( gemm_nt_dmma_pers_kernel<GEMM_CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM ) );
-  c->use_pers = getenv( "B200_GEMM_PERSISTENT" ) != nullptr;     /* experimental, off: measured 28.3 vs 32.9 TFLOP/s at K = 512 (better only for K <= 128), 128^3 factor 752 vs 673 ms */ c->pers_grid = c->prop.multiProcessorCount * 3;
   CKN( cudaMalloc( &c->dZeros, 128 * 8 ) ); CKN( cudaMemset( c->dZeros, 0, 128 * 8 ) );
-  c->use_bulk = getenv( "B200_GEMM_CPASYNC" ) == nullptr;
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LDLT_SMEM ) );
   CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
@@ -579,7 +574,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           double* Bp = Lb + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld;
           double* Wp = TWO ? Ub + m.lptr + ( j0 + nb ) + ( int64_t )j0 * m.ld : nullptr;
           if ( LD ) { /* W21 = A21 T' into the second panel first, then L21 = A21 T2' in place (two launches: the second overwrites what the first reads) */
-            if ( nb == NB && c->use_bulk ) {
+            if ( nb == NB ) {
               double dummy = 0; size_t ntask = gt.size();
               add_gemm( gt, tbt, ts, dummy, Wp, m.ld, Bp, m.ld, inv, nb, below, nb, nb, 0, 0 );
               if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
@@ -597,7 +592,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
             tflops += 2.0 * below * nb * nb;
             continue;
           }
-          if ( nb == NB && c->use_bulk ) {   /* X = B T' on the tensor pipe: C = A B' with C = A = the rows below, B = the inverse diagonal block (in place: one CTA owns whole rows) */
+          if ( nb == NB ) {   /* X = B T' on the tensor pipe: C = A B' with C = A = the rows below, B = the inverse diagonal block (in place: one CTA owns whole rows) */
             double dummy = 0; const size_t ntask = gt.size();
             add_gemm( gt, tbt, ts, dummy, Bp, m.ld, Bp, m.ld, LU ? inv2 : inv, nb, below, nb, nb, 0, 0 );
             if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
@@ -1025,14 +1020,9 @@ static int run_factor( b200_ctx* c ) {
       case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;
       case LK_DIAG_S: potrf_diag_small_kernel<<<( unsigned )l.count, 256, POTRF_S_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr ); break;
       case LK_TRSM: trsm_rows_kernel<<<( unsigned )l.count, 256, TRSM_SMEM, ls>>>( c->trsm_tasks.d, c->trsm_tiles.d + l.first ); break;
-      case LK_TRSM_MMA:
-        if ( c->use_pers ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<int64_t>( l.count, c->pers_grid ), BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, ( int )l.count, c->dZeros );
-        else gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
-        break;
+      case LK_TRSM_MMA: gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros ); break;
       case LK_GEMM_BIG:
-        if ( c->use_bulk && c->use_pers ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<int64_t>( l.count, c->pers_grid ), BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, ( int )l.count, c->dZeros );
-        else if ( c->use_bulk ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
-        else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )l.count, GEMM_THREADS, BIG_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first );
+        gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )l.count, BULK_THREADS, BULK_SMEM, ls>>>( c->gemm_tasks.d, c->tiles_big.d + l.first, c->dZeros );
         gemm_flops += l.flops; gemm_launches++; break;
       case LK_NOP: break;
       case LK_XFER_CB: case LK_BCAST: case LK_GATHER: {
@@ -1369,7 +1359,7 @@ extern "C" int b200_factor_colnorms( b200_ctx_t* c, double* colsq ) {
 
 /* ---- micro-benchmarks: the FP64 roof of OUR kernel and the HBM copy roof */
 extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, int iters ) {
-  if ( !c || m <= 0 || n <= 0 || k <= 0 ) return -1.0;
+  if ( !c || m <= 0 || n <= 0 || k <= 0 || ( m & 1 ) || ( n & 1 ) ) return -1.0;      /* even leading dimensions: 16-byte aligned bulk copies */
   cudaSetDevice( c->device );
   double *A, *B, *C;
   if ( cudaMalloc( &A, ( size_t )m * k * 8 ) || cudaMalloc( &B, ( size_t )n * k * 8 ) || cudaMalloc( &C, ( size_t )m * n * 8 ) ) return -1.0;
@@ -1380,69 +1370,13 @@ extern "C" double b200_bench_dgemm_tflops( b200_ctx_t* c, int m, int n, int k, i
   float best = 1e30f;
   for ( int it = 0; it < iters + 2; it++ ) {
     cudaEventRecord( c->ev0, c->stream );
-    if ( dtb.n ) {
-      if ( c->use_bulk && c->use_pers && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_pers_kernel<GEMM_CFG><<<( unsigned )std::min<size_t>( dtb.n, c->pers_grid ), BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, ( int )dtb.n, c->dZeros );
-      else if ( c->use_bulk && m % 2 == 0 && n % 2 == 0 ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )dtb.n, BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, c->dZeros );
-      else gemm_nt_dmma_kernel<GEMM_CFG><<<( unsigned )dtb.n, GEMM_THREADS, BIG_SMEM, c->stream>>>( dgt.d, dtb.d );
-    }
+    if ( dtb.n ) gemm_nt_dmma_bulk_kernel<GEMM_CFG><<<( unsigned )dtb.n, BULK_THREADS, BULK_SMEM, c->stream>>>( dgt.d, dtb.d, c->dZeros );
     cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
     float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
   }
   dgt.release(); dtb.release(); dts.release(); cudaFree( A ); cudaFree( B ); cudaFree( C );
   if ( cudaGetLastError() != cudaSuccess ) return -1.0;
   return 2.0 * m * n * ( double )k / ( best * 1e-3 ) / 1e12;
-}
-
-/* tuning aid: the same product with different tile configurations of gemm_nt_dmma_kernel */
-template <int BM, int BN, int WM, int WN, int ST, int BK = 16>
-static double bench_variant( b200_ctx* c, int m, int n, int k, int iters ) {
-  constexpr int SMEM = ST * BK * ( BM + 4 + BN + 4 ) * 8;
-  constexpr int NT = ( BM / WM ) * ( BN / WN ) * 32;
-  if ( cudaFuncSetAttribute( gemm_nt_dmma_kernel<BM, BN, WM, WN, ST, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM ) != cudaSuccess ) return -1.0;
-  double *A, *B, *C;
-  if ( cudaMalloc( &A, ( size_t )m * k * 8 ) || cudaMalloc( &B, ( size_t )n * k * 8 ) || cudaMalloc( &C, ( size_t )m * n * 8 ) ) return -1.0;
-  cudaMemset( A, 0, ( size_t )m * k * 8 ); cudaMemset( B, 0, ( size_t )n * k * 8 ); cudaMemset( C, 0, ( size_t )m * n * 8 );
-  GemmTask t; t.C = C; t.A = A; t.B = B; t.ldc = m; t.lda = m; t.ldb = n; t.M = m; t.N = n; t.K = k; t.lower = 0; t.diag = 0; t.mode = 0;
-  std::vector<GemmTask> gt( 1, t ); std::vector<Tile> tl;
-  for ( int tn = 0; tn * BN < n; tn++ ) for ( int tm = 0; tm * BM < m; tm++ ) { Tile x; x.task = 0; x.tm = ( unsigned short )tm; x.tn = ( unsigned short )tn; tl.push_back( x ); }
-  DevVec<GemmTask> dgt; DevVec<Tile> dtl; dgt.upload( gt ); dtl.upload( tl );
-  float best = 1e30f;
-  for ( int it = 0; it < iters + 2; it++ ) {
-    cudaEventRecord( c->ev0, c->stream );
-    gemm_nt_dmma_kernel<BM, BN, WM, WN, ST, BK><<<( unsigned )dtl.n, NT, SMEM, c->stream>>>( dgt.d, dtl.d );
-    cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
-    float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
-  }
-  cudaError_t e = cudaGetLastError();
-  dgt.release(); dtl.release(); cudaFree( A ); cudaFree( B ); cudaFree( C );
-  if ( e != cudaSuccess ) { set_err( "variant: %s", cudaGetErrorString( e ) ); return -1.0; }
-  return 2.0 * m * n * ( double )k / ( best * 1e-3 ) / 1e12;
-}
-extern "C" double b200_bench_dgemm_variant( b200_ctx_t* c, int variant, int m, int n, int k, int iters ) {
-  if ( !c ) return -1.0;
-  cudaSetDevice( c->device );
-  switch ( variant ) {
-    case 0: return bench_variant<128, 128, 64, 32, 4>( c, m, n, k, iters );
-    case 1: return bench_variant<128, 128, 32, 32, 4>( c, m, n, k, iters );
-    case 2: return bench_variant<128, 128, 32, 64, 4>( c, m, n, k, iters );
-    case 3: return bench_variant<128, 128, 32, 32, 3>( c, m, n, k, iters );
-    case 4: return bench_variant<256, 128, 64, 32, 3>( c, m, n, k, iters );
-    case 5: return bench_variant<128, 128, 32, 16, 4>( c, m, n, k, iters );
-    case 6: return bench_variant<64, 64, 32, 32, 4>( c, m, n, k, iters );
-    case 7: return bench_variant<64, 64, 16, 32, 4>( c, m, n, k, iters );
-    case 8: return bench_variant<128, 64, 32, 32, 4>( c, m, n, k, iters );
-    case 9: return bench_variant<64, 64, 16, 32, 3>( c, m, n, k, iters );
-    case 10: return bench_variant<64, 128, 16, 32, 4>( c, m, n, k, iters );
-    case 11: return bench_variant<64, 64, 16, 32, 2, 32>( c, m, n, k, iters );
-    case 12: return bench_variant<64, 64, 16, 32, 3, 32>( c, m, n, k, iters );
-    case 13: return bench_variant<64, 64, 32, 16, 4>( c, m, n, k, iters );
-    case 14: return bench_variant<128, 128, 32, 32, 3, 32>( c, m, n, k, iters );
-    case 15: return bench_variant<64, 64, 16, 16, 4>( c, m, n, k, iters );
-    case 16: return bench_variant<128, 64, 32, 16, 4>( c, m, n, k, iters );
-    case 17: return bench_variant<64, 64, 16, 32, 6>( c, m, n, k, iters );
-    case 18: return bench_variant<32, 64, 16, 16, 4>( c, m, n, k, iters );
-    default: return -1.0;
-  }
 }
 
 /* DMMA throughput as a function of resident warps per SM and independent accumulators per warp */

@@ -1,4 +1,4 @@
-"""production DMMA update kernel, TFLOP/s at a few shapes (B200_GEMM_PERSISTENT=1 selects the experimental persistent-CTA kernel)"""
+"""production DMMA update kernel, TFLOP/s at a few shapes"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import __graft_entry__ as g
