@@ -445,6 +445,14 @@ def test_headline_shape_properties_at_64cubed(mc):
         p = mc.panel_view(flat, d["lptr"][sn], f, k)
         tr += float((np.tril(p[:k]) ** 2).sum() + (p[k:] ** 2).sum())
     assert abs(tr - 6.0 * n) <= 1e-9 * 6.0 * n          # ||L||_F^2 = trace(A)
+    # the factor itself, panel by panel, against the CPU multifrontal oracle (OpenBLAS potrf / trsm / syrk: another summation order)
+    worst = 0.0
+    for sn in range(d["ns"]):
+        k = d["sn_start"][sn + 1] - d["sn_start"][sn]; f = d["rowptr"][sn + 1] - d["rowptr"][sn]
+        g = mc.panel_view(flat, d["lptr"][sn], f, k); o = mc.panel_view(panels, d["lptr"][sn], f, k)
+        g = np.vstack([np.tril(g[:k]), g[k:]]); o = np.vstack([np.tril(o[:k]), o[k:]])
+        worst = max(worst, float(np.abs(g - o).max() / max(np.abs(o).max(), 1e-300)))
+    assert worst <= 1e-11, worst
     s.close()
 
 

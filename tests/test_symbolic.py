@@ -163,3 +163,30 @@ def test_order_nd_standalone_is_a_permutation_and_deterministic(mc):
         assert r == 0 and sorted(p.tolist()) == list(range(n))
         out.append(p)
     assert np.array_equal(out[0], out[1])      # same ordering regardless of the thread count
+
+
+@pytest.mark.parametrize("name,gen", [("convdiff27_9", lambda: stencils.convdiff27_full(9)), ("convdiff27_12x7x5", lambda: stencils.convdiff27_full(12, 7, 5))])
+def test_lu_fill_equals_superlu_fill_on_the_same_ordering(mc, name, gen):
+    """nnz(L) and nnz(U) for a given ordering against an INDEPENDENT sparse LU (north_star: "bit-exact ... nnz(L)/nnz(U) given the same
+    ordering"): SuperLU (scipy) factors P A P' with its own column ordering switched off, no supernode relaxation and diagonal pivots
+    (the matrices are diagonally dominant, so no row interchange changes the structure).  For a structurally symmetric matrix its L and U
+    then hold exactly the fill of the symbolic Cholesky of the pattern -- the column counts of this repo's analysis."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    n, cp, ri, v = gen()
+    S = mc.analyze(n, cp, ri, mc.KIND_LU, relax=False)
+    d = sym_dict(mc, S)
+    A = stencils.to_scipy(n, cp, ri, v, False).tocsc()
+    P = d["perm"]
+    Ap = A[P][:, P].tocsc()
+    lu = sla.splu(Ap, permc_spec="NATURAL", diag_pivot_thresh=0.0, relax=1, panel_size=1, options=dict(SymmetricMode=False))
+    assert np.array_equal(lu.perm_r, np.arange(n)) and np.array_equal(lu.perm_c, np.arange(n)), "SuperLU pivoted: the comparison needs diagonal pivots"
+    Ls = lu.L.tocsc(); Us = lu.U.tocsc()
+    Ls.eliminate_zeros(); Us.eliminate_zeros()
+    cc = d["colcount"].astype(np.int64)                     # entries of column j of L, diagonal included
+    assert int(d["nnzL"]) == int(cc.sum())
+    # structural fill: SuperLU stores every structural nonzero it computed; numerical cancellation to exact zero does not occur on these matrices
+    assert np.array_equal(np.diff(Ls.indptr), cc), "column counts of L differ from SuperLU's"
+    assert np.array_equal(np.diff(Us.tocsr().indptr), cc), "row counts of U differ from SuperLU's (U' has the structure of L)"
+    assert Ls.nnz == d["nnzL"] and Us.nnz == d["nnzL"]
+    mc.lib().b200_symbolic_free(S)
