@@ -179,112 +179,83 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
 }
 
 /* ---------------------------------------------------- diagonal block: LL'
- * Cholesky of a 64 x 64 block (narrower blocks: identity beyond nb), then the inverse of the triangular factor (used by the row update
- * and the solves).  This kernel is the head of the dependency chain of every panel, so it is built for latency -- and to FIT THE
- * INSTRUCTION CACHE: the first version was one fully unrolled 64-column elimination (~12 000 instructions, 42 us per block: the code
- * streamed through the instruction cache once).  Now the block lives in shared memory and is eliminated in eight panels of 8 columns:
- *   (a) panel: 64 threads, thread = row, its 8 panel entries in registers, unrolled over the 8 columns; ONE 64-thread barrier per column
- *       (every row publishes l(r,j) and its current a(r,j+1), from which all threads form the next pivot themselves); rsqrt instead of
- *       sqrt + divide;
- *   (b) rank-8 update of the rows and columns behind the panel by all 256 threads (rolled loop, operands from shared memory; per entry
- *       the same FMA sequence as column-by-column elimination);
- * then the inverse column by column: 4 adjacent lanes share a column (partial dot products joined by two shuffles), a warp owns 8 columns
- * and needs no block-wide barrier at all. */
-constexpr int POTRF_THREADS = 256;
-constexpr int PF_LD = NB + 1;
-constexpr int POTRF_SMEM = ( 2 * NB * PF_LD + 5 * NB ) * 8;
+ * Cholesky of an nb x nb (nb<=64) block, then the inverse of the triangular factor (used by the
+ * row update and the solves).  This kernel is the head of the dependency chain of every panel, so it
+ * is built for latency: 128 threads, the lane pair (2r, 2r+1) keeps row r of the block in registers
+ * (even / odd columns); one barrier per column -- every row publishes l(r,j) and its current
+ * a(r,j+1), from which all threads form the next pivot themselves; the inverse is formed column by
+ * column (a lane pair per column, partial sums joined by one shuffle) from the factor in shared memory. */
+constexpr int POTRF_THREADS = 128;
 __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
-  extern __shared__ double dsm[];
-  double ( *As )[PF_LD] = reinterpret_cast<double ( * )[PF_LD]>( dsm );                          /* the block, row-major: As[r][c]            */
-  double ( *Xs )[PF_LD] = reinterpret_cast<double ( * )[PF_LD]>( dsm + NB * PF_LD );              /* inverse of the factor, Xs[i][c] = X(i,c)  */
-  double ( *colv )[NB] = reinterpret_cast<double ( * )[NB]>( dsm + 2 * NB * PF_LD );              /* l(:,j), double-buffered by column parity  */
-  double ( *nxt )[NB] = reinterpret_cast<double ( * )[NB]>( dsm + 2 * NB * PF_LD + 2 * NB );      /* a(:,j+1) before the update by column j    */
-  double* rdiag = dsm + 2 * NB * PF_LD + 4 * NB;                                                /* 1 / l(i,i)                                */
+  constexpr int H = NB / 2;
+  __shared__ double Ls[NB][NB + 1];      /* finished factor, row-major             */
+  __shared__ double colv[2][NB];         /* l(:,j), double-buffered by j parity    */
+  __shared__ double nxt[2][NB];          /* a(:,j+1) before the update by column j */
+  __shared__ double rdiag[NB];           /* 1 / l(i,i)                             */
   const DiagTask t = tasks[blockIdx.x];
-  const int nb = t.nb, tid = threadIdx.x;
-  for ( int e = tid; e < NB * NB; e += POTRF_THREADS ) {
-    const int r = e & ( NB - 1 ), c = e >> 6;
-    As[r][c] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( r == c ? 1.0 : 0.0 );
-    Xs[r][c] = 0.0;
-  }
+  const int nb = t.nb, r = threadIdx.x >> 1, h = threadIdx.x & 1;
+  double a[H];                           /* a[i] = A(r, 2i+h) */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) { const int c = 2 * i + h; a[i] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( c == r ? 1.0 : 0.0 ); }   /* beyond nb: identity */
+  if ( h == 0 ) nxt[0][r] = a[0];
   __syncthreads();
-  for ( int jp = 0; jp < NB; jp += 8 ) {
-    if ( jp < nb ) {                     /* uniform over the CTA: narrow blocks stop early (the rest is the identity) */
-      if ( tid < NB ) {                  /* (a) the panel of columns jp .. jp+7 */
-        const int r = tid;
-        double p[8];
+  double dj = nxt[0][0];                 /* pivot of the current column, known to every thread */
+  bool bad = false;
 #pragma unroll
-        for ( int q = 0; q < 8; q++ ) p[q] = As[r][jp + q];
-        double dcur = As[jp][jp];
-        bool bad = false; int badcol = 0;
-#pragma unroll
-        for ( int q = 0; q < 8; q++ ) {
-          const int j = jp + q;
-          if ( !( dcur > 0.0 ) ) { if ( !bad ) { bad = true; badcol = j; } dcur = 1.0; }
-          const double rs = rsqrt( dcur );
-          const double l = r > j ? p[q] * rs : ( r == j ? dcur * rs : 0.0 );
-          p[q] = l;
-          colv[q & 1][r] = l;
-          if ( r == j ) rdiag[j] = rs;
-          if ( q < 7 ) nxt[q & 1][r] = p[q + 1];
-          asm volatile( "bar.sync 1, 64;\n" ::: "memory" );
-          if ( q < 7 ) {
-            const double* cv = colv[q & 1];
-            const double ln = cv[j + 1];
-            dcur = fma( -ln, ln, nxt[q & 1][j + 1] );
-#pragma unroll
-            for ( int u = q + 1; u < 8; u++ ) p[u] = fma( -l, cv[jp + u], p[u] );
-          }
-        }
-#pragma unroll
-        for ( int q = 0; q < 8; q++ ) As[r][jp + q] = p[q];
-        if ( bad && r == 0 ) atomicCAS( err, 0, t.col + badcol + 1 );
-      }
+  for ( int j = 0; j < NB; j++ ) {
+    if ( j < nb ) {                      /* uniform over the CTA: small blocks stop early */
+      if ( !( dj > 0.0 ) ) { bad = true; dj = 1.0; }
+      const double rs = rsqrt( dj );     /* one reciprocal square root per column; l = a * rs instead of a division */
+      const double sj = dj * rs;
+      if ( h == ( j & 1 ) ) {            /* the lane that holds column j of its row */
+        const double l = ( r > j ) ? a[j >> 1] * rs : ( r == j ? sj : 0.0 );
+        a[j >> 1] = l;
+        colv[j & 1][r] = l;
+        if ( r == j ) rdiag[j] = rs;
+      } else if ( j + 1 < NB ) nxt[( j + 1 ) & 1][r] = a[( j + 1 ) >> 1];
       __syncthreads();
-      {                                  /* (b) rows / columns behind the panel: a(r,c) -= sum_q l(r,q) l(c,q) */
-        const int r = tid & ( NB - 1 ), cq = tid >> 6;
-        if ( r >= jp + 8 ) {
-          double lr[8];
+      if ( j + 1 < NB ) {
+        const double* cv = colv[j & 1];
+        const double l = cv[r], ln = cv[j + 1];
+        dj = nxt[( j + 1 ) & 1][j + 1] - ln * ln;          /* next pivot */
 #pragma unroll
-          for ( int q = 0; q < 8; q++ ) lr[q] = As[r][jp + q];
-          for ( int c = jp + 8 + cq; c <= r; c += 4 ) {
-            double sacc = As[r][c];
-#pragma unroll
-            for ( int q = 0; q < 8; q++ ) sacc = fma( -lr[q], As[c][jp + q], sacc );
-            As[r][c] = sacc;
-          }
-        }
+        for ( int i = ( j + 1 ) >> 1; i < H; i++ ) { const int c = 2 * i + h; if ( c > j ) a[i] -= l * cv[c]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
       }
-      __syncthreads();
+      if ( bad && threadIdx.x == 0 ) { atomicCAS( err, 0, t.col + j + 1 ); bad = false; }
     }
   }
-  if ( tid < NB && tid >= nb ) rdiag[tid] = 1.0;
-  /* the factor goes back to the panel */
-  for ( int e = tid; e < NB * NB; e += POTRF_THREADS ) {
-    const int r = e & ( NB - 1 ), c = e >> 6;
-    if ( r < nb && c <= r ) t.A[r + ( int64_t )c * t.lda] = As[r][c];
+  /* store L, publish it row-major */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) {
+    const int c = 2 * i + h;
+    Ls[r][c] = ( c <= r ) ? a[i] : 0.0;
+    if ( r < nb && c <= r ) t.A[r + ( int64_t )c * t.lda] = a[i];
   }
   __syncthreads();
-  /* inverse X = inv(L): lanes 4c .. 4c+3 own column c;  x(c,c) = 1/l(c,c),  x(i,c) = -( sum_{q=c}^{i-1} l(i,q) x(q,c) ) / l(i,i) */
-  {
-    const int c = tid >> 2, h = tid & 3;
-    const int c_lo = ( tid >> 5 ) * 8;   /* first column of this warp: rows above it are zero for the whole warp */
-    for ( int i = c_lo; i < nb; i++ ) {
+  /* inverse X = inv(L): lane pair (c, h) owns column c;  x(c,c) = 1/l(c,c),  x(i,c) = -( sum_{q=c}^{i-1} l(i,q) x(q,c) ) / l(i,i);
+   * each lane keeps the x(q,c) with q = h (mod 2) and sums over those */
+  const int c = r;
+  double x[H];                           /* x[i] = X(2i+h, c) */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) x[i] = 0.0;
+#pragma unroll
+  for ( int i = 0; i < NB; i++ ) {
+    if ( i < nb ) {
       double s0 = 0.0, s1 = 0.0;
-      if ( i > c ) {
-        int q = c + h;
-        for ( ; q + 4 < i; q += 8 ) { s0 = fma( As[i][q], Xs[q][c], s0 ); s1 = fma( As[i][q + 4], Xs[q + 4][c], s1 ); }
-        if ( q < i ) s0 = fma( As[i][q], Xs[q][c], s0 );
+#pragma unroll
+      for ( int qi = 0; 2 * qi < i; qi += 2 ) {      /* rows q = 2qi+h < i; x(q,c) = 0 for q < c, so no predicate on c */
+        if ( 2 * qi + h < i ) s0 += Ls[i][2 * qi + h] * x[qi];
+        if ( 2 * ( qi + 1 ) + h < i ) s1 += Ls[i][2 * ( qi + 1 ) + h] * x[qi + 1];
       }
       double sum = s0 + s1;
       sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
-      sum += __shfl_xor_sync( 0xffffffffu, sum, 2 );
-      if ( h == 0 && c < nb ) { if ( i == c ) Xs[i][c] = rdiag[i]; else if ( i > c ) Xs[i][c] = -sum * rdiag[i]; }
-      __syncwarp();
+      if ( h == ( i & 1 ) ) x[i >> 1] = ( i == c ) ? rdiag[i] : ( i > c ? -sum * rdiag[i] : 0.0 );
     }
   }
-  __syncthreads();
-  for ( int e = tid; e < nb * nb; e += POTRF_THREADS ) { const int row = e % nb, c = e / nb; t.inv[row + c * nb] = Xs[row][c]; }
+  if ( c < nb ) {
+#pragma unroll
+    for ( int i = 0; i < H; i++ ) { const int row = 2 * i + h; if ( row < nb ) t.inv[row + c * nb] = x[i]; }
+  }
 }
 
 /* The same operation with rolled loops and the block in shared memory: a few hundred instructions instead of

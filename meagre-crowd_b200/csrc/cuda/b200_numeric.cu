@@ -188,7 +188,6 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   CKN( cudaFuncSetAttribute( getrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GETRF_SMEM ) );
   CKN( cudaFuncSetAttribute( ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LDLT_SMEM ) );
   CKN( cudaFuncSetAttribute( potrf_diag_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_S_SMEM ) );
-  CKN( cudaFuncSetAttribute( potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM ) );
   CKN( cudaFuncSetAttribute( small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM ) );
   c->use_small_front = getenv( "B200_NO_SMALL_FRONT" ) == nullptr;
   c->replicate = getenv( "B200_REPLICATE_FACTOR" ) != nullptr;
@@ -1016,7 +1015,7 @@ static int run_factor( b200_ctx* c ) {
       case LK_DIAG:
         if ( LD ) ldlt_diag_kernel<<<( unsigned )l.count, 256, LDLT_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert, c->dErr );
         else if ( LU ) getrf_diag_kernel<<<( unsigned )l.count, 256, GETRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dTiny, c->dPert, c->dErr );
-        else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, POTRF_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr );
+        else potrf_diag_kernel<<<( unsigned )l.count, POTRF_THREADS, 0, ls>>>( c->diag_tasks.d + l.first, c->dErr );
         break;
       case LK_SMALL_FRONT: small_front_kernel<<<( unsigned )l.count, 256, SF_SMEM, ls>>>( c->small_sns.d + l.first, c->sn.d, c->dL, c->dInv, c->dCB[l.depth & 1], c->dErr ); break;
       case LK_DIAG_S: potrf_diag_small_kernel<<<( unsigned )l.count, 256, POTRF_S_SMEM, ls>>>( c->diag_tasks.d + l.first, c->dErr ); break;
@@ -1457,7 +1456,7 @@ extern "C" double b200_bench_potrf_us( b200_ctx_t* c, int which, int nb, int nta
   for ( int it = 0; it < iters + 2; it++ ) {
     cudaMemcpyAsync( A, A0, h.size() * 8, cudaMemcpyDeviceToDevice, c->stream );
     cudaEventRecord( c->ev0, c->stream );
-    if ( which == 0 ) potrf_diag_kernel<<<ntasks, POTRF_THREADS, POTRF_SMEM, c->stream>>>( dtk, err );
+    if ( which == 0 ) potrf_diag_kernel<<<ntasks, POTRF_THREADS, 0, c->stream>>>( dtk, err );
     else potrf_diag_small_kernel<<<ntasks, 256, POTRF_S_SMEM, c->stream>>>( dtk, err );
     cudaEventRecord( c->ev1, c->stream ); cudaEventSynchronize( c->ev1 );
     float ms; cudaEventElapsedTime( &ms, c->ev0, c->ev1 ); if ( it >= 2 && ms < best ) best = ms;
