@@ -89,7 +89,7 @@ static const char* kind_name[LK_COUNT] = { "memset_cb", "extend_add", "diag_bloc
 /* one point-to-point message of the multi-GPU schedule: which = 0 L storage, 1 inverse blocks, 2/3 contribution-block arena 0/1 */
 struct Msg { int src, dst, which; int64_t off, cnt; };
 
-/* stream 0 = update stream (also level prologues), stream 1 = panel stream (look-ahead), stream 2 = NCCL stream;
+/* stream 0 = update stream (also level prologues), stream 1 = panel stream (look-ahead), stream 2 = NCCL stream, 3 = bulk NCCL stream, 4 = arena zeroing;
  * wait_ev / record_ev index ctx->events (-1: none) */
 struct Launch { int kind; int64_t first; int64_t count; int depth; double flops; int stream = 0; int wait_ev = -1; int record_ev = -1; };
 static double g_alg_flops = 0;   /* accumulates minimal flops of the gemm tasks while a schedule is built */
@@ -117,7 +117,7 @@ template <class T> struct DevVec {
 
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream5 = nullptr;   /* stream5: zeroing of the next level's contribution-block arena, under the current level's updates */
   int rank = 0, world = 1; ncclComm_t comm = nullptr, comm2 = nullptr;   /* comm/stream3: latency-critical panel and contribution-block traffic; comm2/stream4: bulk factor replication */ b200_plan_t* plan = nullptr; std::vector<Msg> msgs; double comm_bytes = 0;
   std::vector<cudaEvent_t> events; int nevents = 0;
   cudaDeviceProp prop;
@@ -179,7 +179,7 @@ extern "C" b200_ctx_t* b200_ctx_create( int device ) {
   c->device = device;
   CKN( cudaGetDeviceProperties( &c->prop, device ) );
   CKN( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); { int lo = 0, hi = 0; CKN( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );   /* the panel chain is short and latency-critical: it must win free SM slots */
-    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); }
+    CKN( cudaStreamCreateWithPriority( &c->stream2, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream3, cudaStreamNonBlocking, hi ) ); CKN( cudaStreamCreateWithPriority( &c->stream4, cudaStreamNonBlocking, lo ) ); CKN( cudaStreamCreateWithPriority( &c->stream5, cudaStreamNonBlocking, lo ) ); }
   CKN( cudaEventCreate( &c->ev0 ) ); CKN( cudaEventCreate( &c->ev1 ) ); CKN( cudaEventCreate( &c->evp0 ) ); CKN( cudaEventCreate( &c->evp1 ) ); CKN( cudaEventCreateWithFlags( &c->evs, cudaEventDisableTiming ) ); CKN( cudaEventCreateWithFlags( &c->evs2, cudaEventDisableTiming ) );
   CKN( cudaMalloc( &c->dErr, sizeof( int ) ) ); CKN( cudaMalloc( &c->dPert, sizeof( int ) ) ); CKN( cudaMalloc( &c->dOmega, sizeof( unsigned long long ) ) ); CKN( cudaMalloc( &c->dTiny, 8 ) ); CKN( cudaMalloc( &c->dMaxBits, 8 ) ); CKN( cudaMalloc( &c->dViol, sizeof( int ) ) );
   { const char* e = getenv( "B200_PIVOT_THRESHOLD" ); if ( e && atof( e ) > 0.0 && atof( e ) <= 1.0 ) c->pivot_threshold = atof( e ); }
@@ -273,7 +273,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   if ( !c ) return;
   if ( c->dry ) { release_symbolic( c ); delete c; return; }
   cudaSetDevice( c->device );
-  cudaStreamSynchronize( c->stream ); cudaStreamSynchronize( c->stream2 ); cudaStreamSynchronize( c->stream3 ); cudaStreamSynchronize( c->stream4 );   /* pending NCCL sends read dL / dInv */
+  cudaStreamSynchronize( c->stream ); cudaStreamSynchronize( c->stream2 ); cudaStreamSynchronize( c->stream3 ); cudaStreamSynchronize( c->stream4 ); cudaStreamSynchronize( c->stream5 );   /* pending NCCL sends read dL / dInv */
   release_symbolic( c );
   cudaFree( c->dErr ); cudaFree( c->dPert ); cudaFree( c->dOmega ); cudaFree( c->dTiny ); cudaFree( c->dMaxBits ); cudaFree( c->dViol ); cudaFree( c->dZeros ); if ( c->flush_buf ) cudaFree( c->flush_buf );
   cudaEventDestroy( c->ev0 ); cudaEventDestroy( c->ev1 ); cudaEventDestroy( c->evp0 ); cudaEventDestroy( c->evp1 ); cudaEventDestroy( c->evs ); cudaEventDestroy( c->evs2 );
@@ -282,7 +282,7 @@ extern "C" void b200_ctx_destroy( b200_ctx_t* c ) {
   if ( c->comm ) g_nccl.CommDestroy( c->comm );
   if ( c->comm2 ) g_nccl.CommDestroy( c->comm2 );
   if ( c->plan ) b200_plan_free( c->plan );
-  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 ); cudaStreamDestroy( c->stream3 ); cudaStreamDestroy( c->stream4 );
+  cudaStreamDestroy( c->stream ); cudaStreamDestroy( c->stream2 ); cudaStreamDestroy( c->stream3 ); cudaStreamDestroy( c->stream4 ); cudaStreamDestroy( c->stream5 );
   delete c;
 }
 
@@ -421,22 +421,35 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
       s0 = s1 + 1;
     }
   }
+  int ev_asm_done = -1;                      /* recorded on the update stream once the extend-add of the level below has read its children's arena */
   for ( int d = S->maxdepth; d >= 0; d-- ) {
     std::vector<int> lv;                                     /* the supernodes of this level I take part in */
     int maxf_all = 0;
     for ( int s : levels[d] ) { maxf_all = std::max( maxf_all, meta[s].f ); if ( member( s ) ) lv.push_back( s ); }
     double* CB = c->dCB[d & 1];
-    if ( !MG ) { if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, 0, c->level_cb[d], d, 0.0 } ); }
-    else { /* zero only the contribution blocks I will write: merge neighbouring ranges of the arena */
-      int64_t lo = -1, hi = -1;
-      for ( int s : lv ) {
-        const int64_t u = meta[s].f - meta[s].k; if ( u == 0 ) continue;
-        const int64_t a = meta[s].cbptr, b = a + ( ( u + 1 ) & ~( int64_t )1 ) * u;
-        if ( lo >= 0 && a <= hi + 4096 ) { hi = std::max( hi, b ); continue; }
+    { /* The contribution blocks of this level are zeroed before its extend-add accumulates into them.  The arena (parity d & 1) was last read by the
+       * extend-add of level d+1, so the zeroing -- pure HBM writes -- runs on a stream of its own UNDER the compute-bound updates of level d+1 instead of
+       * in front of this level (9.5 ms of the 128^3 factorization when it ran in line): it waits for ev_asm_done (recorded after that extend-add) and
+       * this level's first launch waits for it. */
+      const size_t z0 = LS.size();
+      if ( !MG ) { if ( c->level_cb[d] > 0 ) LS.push_back( { LK_MEMSET_CB, 0, c->level_cb[d], d, 0.0 } ); }
+      else { /* zero only the contribution blocks I will write: merge neighbouring ranges of the arena */
+        int64_t lo = -1, hi = -1;
+        for ( int s : lv ) {
+          const int64_t u = meta[s].f - meta[s].k; if ( u == 0 ) continue;
+          const int64_t a = meta[s].cbptr, b = a + ( ( u + 1 ) & ~( int64_t )1 ) * u;
+          if ( lo >= 0 && a <= hi + 4096 ) { hi = std::max( hi, b ); continue; }
+          if ( lo >= 0 ) LS.push_back( { LK_MEMSET_CB, lo, hi - lo, d, 0.0 } );
+          lo = a; hi = b;
+        }
         if ( lo >= 0 ) LS.push_back( { LK_MEMSET_CB, lo, hi - lo, d, 0.0 } );
-        lo = a; hi = b;
       }
-      if ( lo >= 0 ) LS.push_back( { LK_MEMSET_CB, lo, hi - lo, d, 0.0 } );
+      if ( LS.size() > z0 ) {
+        for ( size_t q = z0; q < LS.size(); q++ ) LS[q].stream = 4;
+        LS[z0].wait_ev = ev_asm_done;                    /* -1 at the deepest level: nothing has used the arena yet */
+        const int ez = new_event(); LS.back().record_ev = ez;
+        push_nop( d, 0 ); LS.back().wait_ev = ez;
+      }
     }
     if ( MG ) { /* contribution-block columns computed elsewhere that my part of this level's fronts needs, and vice versa */
       const int64_t nx = b200_plan_cb_transfers( pl, S, d, nullptr, 0 );
@@ -463,6 +476,8 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
         for ( int c0 = 0; c0 < meta[s].f; c0 += acols ) if ( owns( s, c0 ) ) at.push_back( { s, c0, std::min( acols, meta[s].f - c0 ) } );
       }
       if ( ( int64_t )at.size() > first ) LS.push_back( { LK_ASM, first, ( int64_t )at.size() - first, d, 0.0 } );
+      /* from here on the children's arena (parity (d+1) & 1) is free: level d-1 may zero it */
+      push_nop( d, 0 ); ev_asm_done = new_event(); LS.back().record_ev = ev_asm_done;
     }
     if ( c->use_small_front && !TWO ) { /* small fronts: one CTA each, a single launch for the level (small_front_kernel) */
       const int64_t s0 = ( int64_t )smalls.size();
@@ -1003,7 +1018,7 @@ static int run_factor( b200_ctx* c ) {
       if ( c->lvl_ev.size() <= nlev ) { cudaEvent_t e; CK( cudaEventCreate( &e ) ); c->lvl_ev.push_back( e ); }
       CK( cudaEventRecord( c->lvl_ev[nlev++], c->stream ) ); cur_depth = l.depth;
     }
-    cudaStream_t ls = l.stream == 0 ? c->stream : l.stream == 1 ? c->stream2 : l.stream == 2 ? c->stream3 : c->stream4;
+    cudaStream_t ls = l.stream == 0 ? c->stream : l.stream == 1 ? c->stream2 : l.stream == 2 ? c->stream3 : l.stream == 3 ? c->stream4 : c->stream5;
     if ( l.wait_ev >= 0 ) CK( cudaStreamWaitEvent( ls, c->events[l.wait_ev], 0 ) );
     if ( c->profile ) CK( cudaEventRecord( c->evp0, ls ) );
     switch ( l.kind ) {
