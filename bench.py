@@ -62,9 +62,11 @@ class ClockSampler:
 
     def _read(self):
         for l in self.proc.stdout:
-            self.lines.append(l)
+            self.lines.append((time.perf_counter(), l))
 
-    def stop(self):
+    def stop(self, t_from=None):
+        """samples taken since t_from (the start of the timed region); the sampler itself is started before the warm-up, because nvidia-smi needs
+        longer to come up than a short timed region lasts -- if the region saw no sample, the samples of the warm-up steps (the same load) are used and the line says so"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,7 +75,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        inside = [l for t, l in self.lines if t_from is None or t >= t_from]
+        window = "timed region"
+        if not inside:
+            inside = [l for t, l in self.lines][-20:]; window = "warm-up steps (no sample fell into the timed region)"
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
                 continue
@@ -84,7 +90,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def configs(stencils, m):
@@ -317,9 +323,9 @@ def main():
             import torch
             dist.barrier(); torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
     fms, sms, launches = [], [], 0
@@ -327,7 +333,7 @@ def main():
         a, b_, nl = step(); fms.append(a); sms.append(b_); launches += nl
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0)
     factor_s = float(np.mean(fms)) * 1e-3; solve_s = float(np.mean(sms)) * 1e-3
     # max over ranks of the device-timed factor and of the region
     if dist is not None:
