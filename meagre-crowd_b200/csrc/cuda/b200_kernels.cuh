@@ -43,6 +43,8 @@ struct DiagTask {
   double* inv;      /* nb x nb, ld nb: inverse of L (Cholesky) / of unit-L (LU)      */
   double* inv2;     /* LU: inverse of U, stored transposed                            */
   int* piv;         /* LU: pivot row (block-local) chosen for each column            */
+  double* inv3;     /* LU: inv(unit-L) with the block's row interchanges folded in as a column permutation (full nb x nb): the rows of the U' panel
+                       below the block are then one tensor-pipe product  U21' = A12' inv3'  like every other row update; NULL: not wanted */
   int col;          /* global column of the block (for error reports)                */
 };
 
@@ -167,12 +169,21 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
       } else {
         /* full block: (di,dj) goes to the L panel (di>=dj, dj pivot), the U' panel
          * (di<dj, di pivot; stored transposed) or the parent's contribution block */
-        for ( int i = lane; i < uc; i += 32 ) {
-          const int di = rel[i];
-          const double v = s[i];
-          if ( di >= dj ) { if ( dj < kp ) Lp[( int64_t )dj * ldp + di] += v; else CBp[( int64_t )( dj - kp ) * ldup + ( di - kp )] += v; }
-          else { if ( di < kp ) Up[( int64_t )di * ldp + dj] += v; else CBp[( int64_t )( dj - kp ) * ldup + ( di - kp )] += v; }
+        auto where = [&]( int di ) -> double* {
+          if ( di >= dj ) return dj < kp ? Lp + ( int64_t )dj * ldp + di : CBp + ( int64_t )( dj - kp ) * ldup + ( di - kp );
+          return di < kp ? Up + ( int64_t )di * ldp + dj : CBp + ( int64_t )( dj - kp ) * ldup + ( di - kp );
+        };
+        int i = lane;
+        for ( ; i + 224 < uc; i += 256 ) {     /* eight independent gather / add / scatter chains per lane in flight, as in the symmetric case */
+          double sv[8], dv[8]; double* dp[8];
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) { sv[q] = s[i + 32 * q]; dp[q] = where( rel[i + 32 * q] ); }
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) dv[q] = *dp[q];
+#pragma unroll
+          for ( int q = 0; q < 8; q++ ) *dp[q] = dv[q] + sv[q];
         }
+        for ( ; i < uc; i += 32 ) *where( rel[i] ) += s[i];
       }
     }
   }
@@ -455,9 +466,15 @@ __global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __re
       __syncwarp();
     }
   }
+  __shared__ int org[NB];            /* org[q]: the column of the untouched tile that the interchanges, applied in order, bring to position q */
+  if ( tid == 0 ) {
+    for ( int q = 0; q < nb; q++ ) org[q] = q;
+    for ( int j = 0; j < nb; j++ ) { const int pj = t.piv[j]; if ( pj != j ) { const int sw = org[j]; org[j] = org[pj]; org[pj] = sw; } }
+  }
   __syncthreads();
   for ( int e = tid; e < nb * nb; e += 256 ) {
     int r = e % nb, c = e / nb;
+    if ( t.inv3 ) t.inv3[r + org[c] * nb] = x[r][c];               /* inv(L) P: column q of inv(L) goes where the interchanges took it from */
     if ( r > c ) t.A[r + ( int64_t )c * t.lda] = a[r][c];          /* unit-lower L, strict part   */
     else t.AU[c + ( int64_t )r * t.lda] = a[r][c];                 /* U (incl. diagonal), as U'   */
     if ( r == c ) t.A[r + ( int64_t )c * t.lda] = 1.0;

@@ -130,7 +130,7 @@ struct b200_ctx {
   int64_t w_rows[2] = { 0, 0 };
   double flops_exact = 0, flops_stored = 0, gemm_alg_flops = 0;
   /* device arrays */
-  double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dVals = nullptr;
+  double *dL = nullptr, *dU = nullptr, *dCB[2] = { nullptr, nullptr }, *dInv = nullptr, *dInv2 = nullptr, *dInv3 = nullptr, *dVals = nullptr;
   int* dPiv = nullptr; int* dErr = nullptr; int* dPert = nullptr; double* dZeros = nullptr; double* dTiny = nullptr; unsigned long long* dMaxBits = nullptr; int* dViol = nullptr; double pivot_threshold = 0.1; bool use_small_front = true, replicate = false; DevVec<int> small_sns;
   DevVec<int64_t> amap, spmv_ptr; DevVec<int> perm, rowidx, relidx, child_list, spmv_col, spmv_src;
   int refine = -1;            /* -1: automatic (see b200_set_refinement) */
@@ -251,11 +251,11 @@ extern "C" b200_ctx_t* b200_ctx_create_dry( int rank, int world ) {
 static void release_symbolic( b200_ctx* c ) {
   DryGuard dg( c->dry );
   if ( c->dry ) {
-    c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr; c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr;
+    c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dInv3 = c->dVals = nullptr; c->dPiv = nullptr; c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr;
     c->launches.clear(); c->slaunches.clear(); c->nevents = 0; c->msgs.clear(); if ( c->plan ) { b200_plan_free( c->plan ); c->plan = nullptr; }
     return;
   }
-  cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dVals ); cudaFree( c->dPiv );
+  cudaFree( c->dL ); if ( c->dU ) cudaFree( c->dU ); cudaFree( c->dCB[0] ); cudaFree( c->dCB[1] ); cudaFree( c->dInv ); cudaFree( c->dInv2 ); cudaFree( c->dInv3 ); c->dInv3 = nullptr; cudaFree( c->dVals ); cudaFree( c->dPiv );
   cudaFree( c->dSinvF ); cudaFree( c->dSinvB ); cudaFree( c->dSinvTmp ); c->dSinvF = c->dSinvB = c->dSinvTmp = nullptr; c->sinv_tasks.release();
   c->dL = c->dU = c->dCB[0] = c->dCB[1] = c->dInv = c->dInv2 = c->dVals = nullptr; c->dPiv = nullptr;
   c->amap.release(); c->spmv_ptr.release(); c->spmv_col.release(); c->spmv_src.release(); c->perm.release(); c->rowidx.release(); c->relidx.release(); c->child_list.release(); c->sn.release();
@@ -363,9 +363,9 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
     c->dL = reinterpret_cast<double*>( ( uintptr_t )1 << 40 ); c->dCB[0] = reinterpret_cast<double*>( ( uintptr_t )2 << 40 ); c->dCB[1] = reinterpret_cast<double*>( ( uintptr_t )3 << 40 );
     c->dInv = reinterpret_cast<double*>( ( uintptr_t )4 << 40 ); c->dSinvF = reinterpret_cast<double*>( ( uintptr_t )5 << 40 ); c->dSinvB = reinterpret_cast<double*>( ( uintptr_t )6 << 40 );
     c->dVals = reinterpret_cast<double*>( ( uintptr_t )7 << 40 );
-    if ( TWO ) { c->dU = reinterpret_cast<double*>( ( uintptr_t )8 << 40 ); c->dInv2 = reinterpret_cast<double*>( ( uintptr_t )9 << 40 ); c->dSinvTmp = reinterpret_cast<double*>( ( uintptr_t )10 << 40 ); c->dPiv = reinterpret_cast<int*>( ( uintptr_t )11 << 40 ); }
+    if ( TWO ) { c->dU = reinterpret_cast<double*>( ( uintptr_t )8 << 40 ); c->dInv2 = reinterpret_cast<double*>( ( uintptr_t )9 << 40 ); if ( LU ) c->dInv3 = reinterpret_cast<double*>( ( uintptr_t )12 << 40 ); c->dSinvTmp = reinterpret_cast<double*>( ( uintptr_t )10 << 40 ); c->dPiv = reinterpret_cast<int*>( ( uintptr_t )11 << 40 ); }
   }
-  const double need = ( double )c->lsize * 8.0 * ( TWO ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( TWO ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( TWO ? 3 : 2 ) + ( double )S->nnzA * 16.0;
+  const double need = ( double )c->lsize * 8.0 * ( TWO ? 2 : 1 ) + ( double )( c->cb_arena[0] + c->cb_arena[1] ) * 8.0 + ( double )invoff * 8.0 * ( LU ? 3 : TWO ? 2 : 1 ) + ( double )sinvoff * 8.0 * ( TWO ? 3 : 2 ) + ( double )S->nnzA * 16.0;
   if ( !c->dry ) {
   size_t freeb = 0, totb = 0; cudaMemGetInfo( &freeb, &totb );
   if ( need > ( double )freeb * 0.97 ) { char a[64], b[64]; snprintf( a, 64, "%.1f", need / 1e9 ); snprintf( b, 64, "%.1f", freeb / 1e9 ); set_err( "factor needs %s GB of HBM, %s GB free", a, b ); return B200_ERR_NOMEM; }
@@ -375,6 +375,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
   for ( int a = 0; a < 2; a++ ) CK( cudaMalloc( &c->dCB[a], std::max<int64_t>( c->cb_arena[a], 2 ) * 8 ) );
   CK( cudaMalloc( &c->dInv, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) );     /* + slack: the bulk copies of an odd-aligned block read one double past it */
   if ( TWO ) { CK( cudaMalloc( &c->dInv2, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dPiv, sizeof( int ) * n ) ); }
+  if ( LU ) CK( cudaMalloc( &c->dInv3, ( std::max<int64_t>( invoff, 1 ) + 16 ) * 8 ) );
   CK( cudaMalloc( &c->dVals, std::max<int64_t>( S->nnzA, 1 ) * 8 ) );
   CK( cudaMalloc( &c->dSinvF, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMalloc( &c->dSinvB, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );
   CK( cudaMemset( c->dSinvF, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) ); CK( cudaMemset( c->dSinvB, 0, ( std::max<int64_t>( sinvoff, 1 ) + 16 ) * 8 ) );     /* padding rows of odd blocks stay zero */
@@ -567,7 +568,7 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
             DiagTask x; x.lda = m.ld; x.nb = nb; x.col = m.c0 + j0;
             x.A = Lb + m.lptr + j0 + ( int64_t )j0 * m.ld; x.AU = TWO ? Ub + m.lptr + j0 + ( int64_t )j0 * m.ld : nullptr;
             x.inv = c->dInv + m.invptr + ( int64_t )( j0 / NB ) * NB * NB; x.inv2 = TWO ? c->dInv2 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
-            x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr;
+            x.piv = LU ? c->dPiv + m.c0 + j0 : nullptr; x.inv3 = LU ? c->dInv3 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB : nullptr;
             dt.push_back( x );
           }
           if ( pass == 0 ) d1 = ( int64_t )dt.size();
@@ -618,10 +619,17 @@ extern "C" int b200_upload_symbolic( b200_ctx_t* c, const b200_symbolic_t* S ) {
           for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
           tflops += ( double )below * nb * nb;
           }
-          if ( LU ) {
-            TrsmTask y; y.B = Wp; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0; y.out = nullptr; y.full = 0;
-            const int id = ( int )tt.size(); tt.push_back( y );
-            for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
+          if ( LU ) { /* rows of the U' panel below the block:  U21' = (A12' P') inv(L)' .  Full blocks: the interchanges are folded into inv3 (getrf_diag), so this
+                       * is the same in-place tensor-pipe product as the L rows (round 2: 51 ms of the 27-pt 96^3 factorization sat in the register-tile kernel) */
+            if ( nb == NB ) {
+              double dummy = 0; const size_t ntask = gt.size();
+              add_gemm( gt, tbt, ts, dummy, Wp, m.ld, Wp, m.ld, c->dInv3 + m.invptr + ( int64_t )( j0 / NB ) * NB * NB, nb, below, nb, nb, 0, 0 );
+              if ( gt.size() > ntask ) { gt.back().mode = 1; g_alg_flops -= 2.0 * below * nb * nb; }
+            } else {
+              TrsmTask y; y.B = Wp; y.ldb = m.ld; y.m = below; y.nb = nb; y.T = inv; y.piv = c->dPiv + m.c0 + j0; y.out = nullptr; y.full = 0;
+              const int id = ( int )tt.size(); tt.push_back( y );
+              for ( int r0 = 0; r0 < below; r0 += 128 ) ttl.push_back( { id, r0 } );
+            }
             tflops += ( double )below * nb * nb;
           }
         }
@@ -1465,7 +1473,7 @@ extern "C" double b200_bench_potrf_us( b200_ctx_t* c, int which, int nb, int nta
   if ( cudaMalloc( &A0, h.size() * 8 ) || cudaMalloc( &A, h.size() * 8 ) || cudaMalloc( &inv, h.size() * 8 ) || cudaMalloc( &err, 4 ) || cudaMalloc( &dtk, sizeof( DiagTask ) * ntasks ) ) return -1.0;
   cudaMemcpy( A0, h.data(), h.size() * 8, cudaMemcpyHostToDevice ); cudaMemset( err, 0, 4 );
   std::vector<DiagTask> tk( ntasks );
-  for ( int t = 0; t < ntasks; t++ ) { tk[t].A = A + t * blk; tk[t].AU = nullptr; tk[t].lda = NB; tk[t].nb = nb; tk[t].inv = inv + t * blk; tk[t].inv2 = nullptr; tk[t].piv = nullptr; tk[t].col = 0; }
+  for ( int t = 0; t < ntasks; t++ ) { tk[t].A = A + t * blk; tk[t].AU = nullptr; tk[t].lda = NB; tk[t].nb = nb; tk[t].inv = inv + t * blk; tk[t].inv2 = nullptr; tk[t].piv = nullptr; tk[t].inv3 = nullptr; tk[t].col = 0; }
   cudaMemcpy( dtk, tk.data(), sizeof( DiagTask ) * ntasks, cudaMemcpyHostToDevice );
   float best = 1e30f;
   for ( int it = 0; it < iters + 2; it++ ) {
