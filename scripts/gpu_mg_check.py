@@ -31,7 +31,7 @@ lv = [l for l in cb.value.decode().splitlines() if l.startswith("levels_ms")]
 for r_ in range(world):
     dist.barrier()
     if r_ == rank and lv:
-        t = lv[0].split(":")[1].split(); print(f"rank {rank} level ms (root last): ... " + " ".join(t[-8:]) + f" | sum {sum(float(x) for x in t):.1f}", flush=True)
+        t = lv[0].split(":")[1].split(); print(f"rank {rank} level ms (deepest first, root last): " + " ".join(t) + f" | sum {sum(float(x) for x in t):.1f}", flush=True)
 A = stencils.to_scipy(n, cp, ri, v, True)
 berr = float(np.abs(A @ x - b).max() / (12.0 * np.abs(x).max() + np.abs(b).max())) if rank == 0 else 0.0
 Lmg = s.read_factor(0)
