@@ -199,8 +199,7 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
 constexpr int POTRF_THREADS = 128;
 __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
   constexpr int H = NB / 2;
-  __shared__ double Ls[NB][NB + 1];      /* finished factor, row-major             */
-  __shared__ double colv[2][NB];         /* l(:,j), double-buffered by j parity    */
+  __shared__ double Ls[NB][NB + 1];      /* the factor, row-major; column j is written by all rows in step j (it doubles as the broadcast of l(:,j)) */
   __shared__ double nxt[2][NB];          /* a(:,j+1) before the update by column j */
   __shared__ double rdiag[NB];           /* 1 / l(i,i)                             */
   const DiagTask t = tasks[blockIdx.x];
@@ -209,6 +208,14 @@ __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const Diag
 #pragma unroll
   for ( int i = 0; i < H; i++ ) { const int c = 2 * i + h; a[i] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( c == r ? 1.0 : 0.0 ); }   /* beyond nb: identity */
   if ( h == 0 ) nxt[0][r] = a[0];
+  /* The inverse X = inv(L) is formed IN THE SAME LOOP, one row per step: row j of L is complete once column j has been published, and
+   * x(j,c) = -( sum_{q=c}^{j-1} l(j,q) x(q,c) ) / l(j,j) only needs that row and the earlier rows of X, which the lane pair (c, h) keeps in
+   * registers (x(q,c) with q = h mod 2).  The two recurrences are independent chains of 64 dependent steps each; interleaved they hide in one
+   * another's latency instead of running back to back (round 2: 42 us -> see profiles/r1_potrf_bench.txt). */
+  const int c = r;
+  double x[H];                           /* x[i] = X(2i+h, c) */
+#pragma unroll
+  for ( int i = 0; i < H; i++ ) x[i] = 0.0;
   __syncthreads();
   double dj = nxt[0][0];                 /* pivot of the current column, known to every thread */
   bool bad = false;
@@ -221,47 +228,35 @@ __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const Diag
       if ( h == ( j & 1 ) ) {            /* the lane that holds column j of its row */
         const double l = ( r > j ) ? a[j >> 1] * rs : ( r == j ? sj : 0.0 );
         a[j >> 1] = l;
-        colv[j & 1][r] = l;
+        Ls[r][j] = l;
         if ( r == j ) rdiag[j] = rs;
       } else if ( j + 1 < NB ) nxt[( j + 1 ) & 1][r] = a[( j + 1 ) >> 1];
       __syncthreads();
       if ( j + 1 < NB ) {
-        const double* cv = colv[j & 1];
-        const double l = cv[r], ln = cv[j + 1];
+        const double l = Ls[r][j], ln = Ls[j + 1][j];
         dj = nxt[( j + 1 ) & 1][j + 1] - ln * ln;          /* next pivot */
 #pragma unroll
-        for ( int i = ( j + 1 ) >> 1; i < H; i++ ) { const int c = 2 * i + h; if ( c > j ) a[i] -= l * cv[c]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
+        for ( int i = ( j + 1 ) >> 1; i < H; i++ ) { const int cc = 2 * i + h; if ( cc > j ) a[i] -= l * Ls[cc][j]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
+      }
+      {                                  /* row j of the inverse */
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for ( int qi = 0; 2 * qi < j; qi += 2 ) {      /* rows q = 2qi+h < j; x(q,c) = 0 for q < c, so no predicate on c */
+          if ( 2 * qi + h < j ) s0 += Ls[j][2 * qi + h] * x[qi];
+          if ( 2 * ( qi + 1 ) + h < j ) s1 += Ls[j][2 * ( qi + 1 ) + h] * x[qi + 1];
+        }
+        double sum = s0 + s1;
+        sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
+        if ( h == ( j & 1 ) ) x[j >> 1] = ( j == c ) ? rs : ( j > c ? -sum * rs : 0.0 );
       }
       if ( bad && threadIdx.x == 0 ) { atomicCAS( err, 0, t.col + j + 1 ); bad = false; }
     }
   }
-  /* store L, publish it row-major */
+  /* store L and the inverse */
 #pragma unroll
   for ( int i = 0; i < H; i++ ) {
-    const int c = 2 * i + h;
-    Ls[r][c] = ( c <= r ) ? a[i] : 0.0;
-    if ( r < nb && c <= r ) t.A[r + ( int64_t )c * t.lda] = a[i];
-  }
-  __syncthreads();
-  /* inverse X = inv(L): lane pair (c, h) owns column c;  x(c,c) = 1/l(c,c),  x(i,c) = -( sum_{q=c}^{i-1} l(i,q) x(q,c) ) / l(i,i);
-   * each lane keeps the x(q,c) with q = h (mod 2) and sums over those */
-  const int c = r;
-  double x[H];                           /* x[i] = X(2i+h, c) */
-#pragma unroll
-  for ( int i = 0; i < H; i++ ) x[i] = 0.0;
-#pragma unroll
-  for ( int i = 0; i < NB; i++ ) {
-    if ( i < nb ) {
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for ( int qi = 0; 2 * qi < i; qi += 2 ) {      /* rows q = 2qi+h < i; x(q,c) = 0 for q < c, so no predicate on c */
-        if ( 2 * qi + h < i ) s0 += Ls[i][2 * qi + h] * x[qi];
-        if ( 2 * ( qi + 1 ) + h < i ) s1 += Ls[i][2 * ( qi + 1 ) + h] * x[qi + 1];
-      }
-      double sum = s0 + s1;
-      sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
-      if ( h == ( i & 1 ) ) x[i >> 1] = ( i == c ) ? rdiag[i] : ( i > c ? -sum * rdiag[i] : 0.0 );
-    }
+    const int cc = 2 * i + h;
+    if ( r < nb && cc <= r ) t.A[r + ( int64_t )cc * t.lda] = a[i];
   }
   if ( c < nb ) {
 #pragma unroll
