@@ -196,24 +196,24 @@ __global__ void __launch_bounds__( 256 ) extend_add_kernel( const AsmTask* __res
  * (even / odd columns); one barrier per column -- every row publishes l(r,j) and its current
  * a(r,j+1), from which all threads form the next pivot themselves; the inverse is formed column by
  * column (a lane pair per column, partial sums joined by one shuffle) from the factor in shared memory. */
-constexpr int POTRF_THREADS = 128;
+constexpr int POTRF_LPR = 4;                         /* lanes per row of the block: 4 lanes x 16 columns (2 x 32 measured 33.4 us: half the instructions per thread per step) */
+constexpr int POTRF_THREADS = NB * POTRF_LPR;
 __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const DiagTask* __restrict__ tasks, int* __restrict__ err ) {
-  constexpr int H = NB / 2;
+  constexpr int LPR = POTRF_LPR, H = NB / LPR;
   __shared__ double Ls[NB][NB + 1];      /* the factor, row-major; column j is written by all rows in step j (it doubles as the broadcast of l(:,j)) */
   __shared__ double nxt[2][NB];          /* a(:,j+1) before the update by column j */
-  __shared__ double rdiag[NB];           /* 1 / l(i,i)                             */
   const DiagTask t = tasks[blockIdx.x];
-  const int nb = t.nb, r = threadIdx.x >> 1, h = threadIdx.x & 1;
-  double a[H];                           /* a[i] = A(r, 2i+h) */
+  const int nb = t.nb, r = threadIdx.x / LPR, h = threadIdx.x % LPR;
+  double a[H];                           /* a[i] = A(r, LPR*i+h) */
 #pragma unroll
-  for ( int i = 0; i < H; i++ ) { const int c = 2 * i + h; a[i] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( c == r ? 1.0 : 0.0 ); }   /* beyond nb: identity */
+  for ( int i = 0; i < H; i++ ) { const int c = LPR * i + h; a[i] = ( r < nb && c <= r ) ? t.A[r + ( int64_t )c * t.lda] : ( c == r ? 1.0 : 0.0 ); }   /* beyond nb: identity */
   if ( h == 0 ) nxt[0][r] = a[0];
   /* The inverse X = inv(L) is formed IN THE SAME LOOP, one row per step: row j of L is complete once column j has been published, and
-   * x(j,c) = -( sum_{q=c}^{j-1} l(j,q) x(q,c) ) / l(j,j) only needs that row and the earlier rows of X, which the lane pair (c, h) keeps in
-   * registers (x(q,c) with q = h mod 2).  The two recurrences are independent chains of 64 dependent steps each; interleaved they hide in one
-   * another's latency instead of running back to back (round 2: 42 us -> see profiles/r1_potrf_bench.txt). */
+   * x(j,c) = -( sum_{q=c}^{j-1} l(j,q) x(q,c) ) / l(j,j) only needs that row and the earlier rows of X, which the lanes (c, h) keep in
+   * registers (x(q,c) with q = h mod LPR).  The two recurrences are independent chains of 64 dependent steps each; interleaved they hide in one
+   * another's latency instead of running back to back (round 2: 42 us -> 33 us with 2 lanes per row; profiles/r1_potrf_bench.txt). */
   const int c = r;
-  double x[H];                           /* x[i] = X(2i+h, c) */
+  double x[H];                           /* x[i] = X(LPR*i+h, c) */
 #pragma unroll
   for ( int i = 0; i < H; i++ ) x[i] = 0.0;
   __syncthreads();
@@ -225,29 +225,30 @@ __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const Diag
       if ( !( dj > 0.0 ) ) { bad = true; dj = 1.0; }
       const double rs = rsqrt( dj );     /* one reciprocal square root per column; l = a * rs instead of a division */
       const double sj = dj * rs;
-      if ( h == ( j & 1 ) ) {            /* the lane that holds column j of its row */
-        const double l = ( r > j ) ? a[j >> 1] * rs : ( r == j ? sj : 0.0 );
-        a[j >> 1] = l;
+      if ( h == ( j % LPR ) ) {          /* the lane that holds column j of its row */
+        const double l = ( r > j ) ? a[j / LPR] * rs : ( r == j ? sj : 0.0 );
+        a[j / LPR] = l;
         Ls[r][j] = l;
-        if ( r == j ) rdiag[j] = rs;
-      } else if ( j + 1 < NB ) nxt[( j + 1 ) & 1][r] = a[( j + 1 ) >> 1];
+      }
+      if ( j + 1 < NB && h == ( ( j + 1 ) % LPR ) ) nxt[( j + 1 ) & 1][r] = a[( j + 1 ) / LPR];
       __syncthreads();
       if ( j + 1 < NB ) {
         const double l = Ls[r][j], ln = Ls[j + 1][j];
         dj = nxt[( j + 1 ) & 1][j + 1] - ln * ln;          /* next pivot */
 #pragma unroll
-        for ( int i = ( j + 1 ) >> 1; i < H; i++ ) { const int cc = 2 * i + h; if ( cc > j ) a[i] -= l * Ls[cc][j]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
+        for ( int i = ( j + 1 ) / LPR; i < H; i++ ) { const int cc = LPR * i + h; if ( cc > j ) a[i] -= l * Ls[cc][j]; }     /* entries right of the diagonal (c > r) are scratch: updating them too saves the predicate */
       }
       {                                  /* row j of the inverse */
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for ( int qi = 0; 2 * qi < j; qi += 2 ) {      /* rows q = 2qi+h < j; x(q,c) = 0 for q < c, so no predicate on c */
-          if ( 2 * qi + h < j ) s0 += Ls[j][2 * qi + h] * x[qi];
-          if ( 2 * ( qi + 1 ) + h < j ) s1 += Ls[j][2 * ( qi + 1 ) + h] * x[qi + 1];
+        for ( int qi = 0; LPR * qi < j; qi += 2 ) {      /* rows q = LPR*qi+h < j; x(q,c) = 0 for q < c, so no predicate on c */
+          if ( LPR * qi + h < j ) s0 += Ls[j][LPR * qi + h] * x[qi];
+          if ( LPR * ( qi + 1 ) + h < j ) s1 += Ls[j][LPR * ( qi + 1 ) + h] * x[qi + 1];
         }
         double sum = s0 + s1;
-        sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
-        if ( h == ( j & 1 ) ) x[j >> 1] = ( j == c ) ? rs : ( j > c ? -sum * rs : 0.0 );
+#pragma unroll
+        for ( int o = 1; o < LPR; o <<= 1 ) sum += __shfl_xor_sync( 0xffffffffu, sum, o );
+        if ( h == ( j % LPR ) ) x[j / LPR] = ( j == c ) ? rs : ( j > c ? -sum * rs : 0.0 );
       }
       if ( bad && threadIdx.x == 0 ) { atomicCAS( err, 0, t.col + j + 1 ); bad = false; }
     }
@@ -255,12 +256,12 @@ __global__ void __launch_bounds__( POTRF_THREADS ) potrf_diag_kernel( const Diag
   /* store L and the inverse */
 #pragma unroll
   for ( int i = 0; i < H; i++ ) {
-    const int cc = 2 * i + h;
+    const int cc = LPR * i + h;
     if ( r < nb && cc <= r ) t.A[r + ( int64_t )cc * t.lda] = a[i];
   }
   if ( c < nb ) {
 #pragma unroll
-    for ( int i = 0; i < H; i++ ) { const int row = 2 * i + h; if ( row < nb ) t.inv[row + c * nb] = x[i]; }
+    for ( int i = 0; i < H; i++ ) { const int row = LPR * i + h; if ( row < nb ) t.inv[row + c * nb] = x[i]; }
   }
 }
 
