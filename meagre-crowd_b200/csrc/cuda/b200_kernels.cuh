@@ -446,21 +446,17 @@ __global__ void __launch_bounds__( 256 ) getrf_diag_kernel( const DiagTask* __re
       const double lr = colv[r];
       for ( int c = j + 1 + cg; c < nb; c += 4 ) a[r][c] -= lr * rowv[c];
     }
-    __syncthreads();
-  }
-  /* x = inverse of unit lower L ; y = inverse of upper U (column by column of the transposes) */
-  {
-    const int col = tid >> 2, part = tid & 3;
-    if ( col < nb && part == 0 ) { x[col][col] = 1.0; y[col][col] = 1.0 / a[col][col]; }
-    __syncwarp();
-    for ( int i = 1; i < nb; i++ ) {
+    { /* row j of x = inverse of the unit lower L and column j of y = inverse of the upper U, in the same step: row j of L (its interchange is done),
+       * column j of U and the pivot are final and no later step touches them, so this chain of 64 dependent steps runs alongside the
+       * elimination instead of behind it (as in potrf_diag).  Four lanes per column `col`; each group only reads its own earlier results. */
+      const int col = tid >> 2, part = tid & 3;
       double s = 0.0, u = 0.0;
-      if ( col < nb && i > col ) for ( int q = col + part; q < i; q += 4 ) { s += a[i][q] * x[q][col]; u += a[q][i] * y[col][q]; }
+      if ( col < nb && j > col ) for ( int q = col + part; q < j; q += 4 ) { s += a[j][q] * x[q][col]; u += a[q][j] * y[col][q]; }
       s += __shfl_xor_sync( 0xffffffffu, s, 1 ); s += __shfl_xor_sync( 0xffffffffu, s, 2 );
       u += __shfl_xor_sync( 0xffffffffu, u, 1 ); u += __shfl_xor_sync( 0xffffffffu, u, 2 );
-      if ( col < nb && i > col && part == 0 ) { x[i][col] = -s; y[col][i] = -u / a[i][i]; }
-      __syncwarp();
+      if ( col < nb && part == 0 ) { if ( j == col ) { x[col][col] = 1.0; y[col][col] = 1.0 / d; } else if ( j > col ) { x[j][col] = -s; y[col][j] = -u / d; } }
     }
+    __syncthreads();
   }
   __shared__ int org[NB];            /* org[q]: the column of the untouched tile that the interchanges, applied in order, bring to position q */
   if ( tid == 0 ) {
